@@ -1,0 +1,768 @@
+// brief_capi.cu — the extern "C" boundary of libbrief_b200 (include/brief_b200.h) and the host-side
+// group bookkeeping: arenas, padded<->packed parameter conversion, work tables, launch sequencing.
+// No torch types cross this boundary; no CPU compute path exists behind it.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/brief_b200.h"
+#include "brief_common.cuh"
+#include "brief_kernels.h"
+
+using namespace brief;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (expr);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(BRIEF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                                         \
+  } while (0)
+#define LAUNCH(expr)      \
+  do {                    \
+    CU(expr);             \
+    g_launches.fetch_add(1); \
+  } while (0)
+#define RC(expr)          \
+  do {                    \
+    int rc__ = (expr);    \
+    if (rc__) return rc__; \
+  } while (0)
+
+constexpr size_t kSmemLimit = 200 * 1024;       // dynamic smem budget of the fp32 kernels
+constexpr size_t kPartialCapBytes = 16u << 20;  // gradient-partial budget per network
+constexpr int kTcTile = 128;                    // samples per tcgen05 tile (UMMA M)
+constexpr int kTcMinTilesPerSlice = 8;
+constexpr int kTcEvalTilesPerBlock = 64;
+constexpr int kBuckets = 9;  // F_PAD / 16 in 1..8
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = std::max<size_t>(count, 1);
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+struct WorkTable {  // block -> (network, local work index) for one kernel family
+  int n = 0;        // networks
+  int blocks = 0;
+  int off_prefix = 0, off_net = 0;  // int offsets into the device table buffer
+};
+
+}  // namespace
+
+struct BriefGroup {
+  int device = 0;
+  int n_nets = 0;
+  std::vector<NetDev> nets;
+  long long total_P = 0, total_axis = 0;
+  size_t total_wpack = 0;
+  DevBuf<NetDev> d_nets;
+  DevBuf<float> d_params, d_grads, d_m, d_v, d_axes, d_partials, d_loss_partials, d_loss_scratch;
+  DevBuf<unsigned char> d_wpack;
+  DevBuf<int> d_fit_tables, d_eval_tables;
+  DevBuf<void*> d_outptrs;
+  bool nets_dirty = true;   // host NetDev array differs from the device copy
+  bool work_dirty = true;   // sampler changed: rebuild the fit decomposition
+  bool wpack_dirty = true;  // params changed since the bf16 operand image was packed
+  bool any_tc = false, any_simt = false;
+  // fit
+  int simt_fit_tm = 0;
+  size_t simt_fit_smem = 0;
+  WorkTable simt_fit, tc_fit[kBuckets], opt;
+  // eval (static)
+  int simt_eval_tm = 0;
+  size_t simt_eval_smem = 0;
+  WorkTable simt_eval, tc_eval[kBuckets];
+};
+
+namespace {
+
+int f4_of(int f) { return (f + 3) & ~3; }
+
+// reference packed order (utils/ModelSave.py:32-51) <-> padded device layout ----------------------
+void packed_to_dev(const NetDev& n, const float* src, float* dst) {
+  std::fill(dst, dst + n.P_dev, 0.f);
+  const int f = n.f, F4 = n.F4, in = n.in_dim;
+  const float* s = src;
+  for (int o = 0; o < f; ++o)
+    for (int c = 0; c < in; ++c) dst[dl_W0(n) + 4 * o + c] = *s++;
+  for (int o = 0; o < f; ++o) dst[dl_b0(n) + o] = *s++;
+  for (int l = 1; l <= n.L - 2; ++l) {
+    for (int o = 0; o < f; ++o)
+      for (int k = 0; k < f; ++k) dst[dl_W(n, l) + o * F4 + k] = *s++;
+    for (int o = 0; o < f; ++o) dst[dl_b(n, l) + o] = *s++;
+  }
+  for (int k = 0; k < f; ++k) dst[dl_Wlast(n) + k] = *s++;
+  dst[dl_blast(n)] = *s++;
+}
+void dev_to_packed(const NetDev& n, const float* src, float* dst) {
+  const int f = n.f, F4 = n.F4, in = n.in_dim;
+  float* d = dst;
+  for (int o = 0; o < f; ++o)
+    for (int c = 0; c < in; ++c) *d++ = src[dl_W0(n) + 4 * o + c];
+  for (int o = 0; o < f; ++o) *d++ = src[dl_b0(n) + o];
+  for (int l = 1; l <= n.L - 2; ++l) {
+    for (int o = 0; o < f; ++o)
+      for (int k = 0; k < f; ++k) *d++ = src[dl_W(n, l) + o * F4 + k];
+    for (int o = 0; o < f; ++o) *d++ = src[dl_b(n, l) + o];
+  }
+  for (int k = 0; k < f; ++k) *d++ = src[dl_Wlast(n) + k];
+  *d++ = src[dl_blast(n)];
+}
+
+int check_net(const BriefGroup* g, int net) {
+  if (!g) return fail(BRIEF_ERR_INVALID, "null group");
+  if (net < 0 || net >= g->n_nets)
+    return fail(BRIEF_ERR_INVALID, "network index %d out of range [0,%d)", net, g->n_nets);
+  return 0;
+}
+
+int use_device(const BriefGroup* g) {
+  CU(cudaSetDevice(g->device));
+  return 0;
+}
+
+int sync_nets(BriefGroup* g, cudaStream_t st) {
+  if (!g->nets_dirty) return 0;
+  CU(cudaMemcpyAsync(g->d_nets.p, g->nets.data(), sizeof(NetDev) * g->n_nets, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  g->nets_dirty = false;
+  return 0;
+}
+
+int upload_tables(DevBuf<int>& buf, const std::vector<int>& tab, cudaStream_t st) {
+  CU(buf.ensure(tab.size()));
+  if (!tab.empty()) {
+    CU(cudaMemcpyAsync(buf.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+struct TableBuilder {
+  std::vector<int> tab;
+  void add(WorkTable& w, const std::vector<int>& prefix, const std::vector<int>& nets) {
+    w.n = (int)nets.size();
+    w.blocks = prefix.empty() ? 0 : prefix.back();
+    w.off_prefix = (int)tab.size();
+    tab.insert(tab.end(), prefix.begin(), prefix.end());
+    w.off_net = (int)tab.size();
+    tab.insert(tab.end(), nets.begin(), nets.end());
+  }
+};
+
+// static decomposition of the dense-grid evaluation (decompress)
+int build_eval_tables(BriefGroup* g, cudaStream_t st) {
+  int tm = 128;
+  for (auto& n : g->nets) {
+    if (n.prec == BRIEF_PREC_BF16) continue;
+    const int t = simt_pick_tm(n.F4, n.L, false, kSmemLimit);
+    if (t == 0)
+      return fail(BRIEF_ERR_UNSUPPORTED, "features=%d exceed the fp32 kernel's shared-memory budget", n.f);
+    tm = std::min(tm, t);
+  }
+  g->simt_eval_tm = tm;
+  g->simt_eval_smem = 0;
+  std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets];
+  for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
+  for (int i = 0; i < g->n_nets; ++i) {
+    const NetDev& n = g->nets[i];
+    if (n.prec == BRIEF_PREC_BF16) {
+      const int b = n.F_PAD / 16;
+      const long long tiles = (n.n_vox + kTcTile - 1) / kTcTile;
+      const long long blocks = (tiles + kTcEvalTilesPerBlock - 1) / kTcEvalTilesPerBlock;
+      if (tp[b].back() + blocks > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "group too large for one launch");
+      tn[b].push_back(i);
+      tp[b].push_back((int)(tp[b].back() + blocks));
+    } else {
+      const long long tiles = (n.n_vox + tm - 1) / tm;
+      if (sp.back() + tiles > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "group too large for one launch");
+      sn.push_back(i);
+      sp.push_back((int)(sp.back() + tiles));
+      g->simt_eval_smem = std::max(g->simt_eval_smem, simt_eval_smem(n.F4, tm));
+    }
+  }
+  TableBuilder tb;
+  tb.add(g->simt_eval, sp, sn);
+  for (int b = 1; b < kBuckets; ++b) tb.add(g->tc_eval[b], tp[b], tn[b]);
+  return upload_tables(g->d_eval_tables, tb.tab, st);
+}
+
+// (re)build the fit decomposition: slices per network, partial arenas, block -> work tables
+int finalize(BriefGroup* g, cudaStream_t st) {
+  if (!g->work_dirty) return sync_nets(g, st);
+  int tm = 128;
+  g->any_simt = g->any_tc = false;
+  for (auto& n : g->nets) {
+    if (n.prec == BRIEF_PREC_BF16) { g->any_tc = true; continue; }
+    g->any_simt = true;
+    const int t = simt_pick_tm(n.F4, n.L, true, kSmemLimit);
+    if (t == 0)
+      return fail(BRIEF_ERR_UNSUPPORTED, "features=%d layers=%d exceed the fp32 kernel's shared-memory budget", n.f, n.L);
+    tm = std::min(tm, t);
+  }
+  g->simt_fit_tm = tm;
+  g->simt_fit_smem = 0;
+  long long slice_total = 0, part_total = 0, idx_total = 0;
+  std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets], op{0}, on;
+  for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
+  for (int i = 0; i < g->n_nets; ++i) {
+    NetDev& n = g->nets[i];
+    if (n.mode == BRIEF_SAMPLE_FULL_BLOCK) {
+      if (n.n_vox > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "block of %lld voxels exceeds the full-block sampler limit", n.n_vox);
+      n.batch = (int)n.n_vox;
+      n.idx_off = 0;
+    } else {
+      n.idx_off = idx_total;
+      idx_total += n.batch;
+    }
+    const bool tc = n.prec == BRIEF_PREC_BF16;
+    const int tile = tc ? kTcTile : tm;
+    const long long n_tiles = ((long long)n.batch + tile - 1) / tile;
+    const long long max_slices = std::max<long long>(1, (long long)(kPartialCapBytes / ((size_t)n.P_dev * 4)));
+    long long tps = (n_tiles + max_slices - 1) / max_slices;
+    if (tc) tps = std::max<long long>(tps, kTcMinTilesPerSlice);
+    tps = std::max<long long>(tps, 1);
+    n.slice_len = (int)(tps * tile);
+    n.n_slices = (int)((n_tiles + tps - 1) / tps);
+    n.slice_off = slice_total;
+    n.part_off = part_total;
+    slice_total += n.n_slices;
+    part_total += (long long)n.n_slices * n.P_dev;
+    if (tc) {
+      const int b = n.F_PAD / 16;
+      tn[b].push_back(i);
+      tp[b].push_back(tp[b].back() + n.n_slices);
+    } else {
+      sn.push_back(i);
+      sp.push_back(sp.back() + n.n_slices);
+      g->simt_fit_smem = std::max(g->simt_fit_smem, simt_fit_smem(n.F4, n.L, tm));
+    }
+    on.push_back(i);
+    op.push_back(op.back() + (n.P_dev + 255) / 256);
+  }
+  TableBuilder tb;
+  tb.add(g->simt_fit, sp, sn);
+  for (int b = 1; b < kBuckets; ++b) tb.add(g->tc_fit[b], tp[b], tn[b]);
+  tb.add(g->opt, op, on);
+  RC(upload_tables(g->d_fit_tables, tb.tab, st));
+  CU(g->d_partials.ensure((size_t)part_total));
+  CU(g->d_loss_partials.ensure((size_t)slice_total));
+  CU(g->d_loss_scratch.ensure((size_t)g->n_nets));
+  g->nets_dirty = true;
+  RC(sync_nets(g, st));
+  g->work_dirty = false;
+  return 0;
+}
+
+int ensure_wpack(BriefGroup* g, cudaStream_t st) {
+  if (!g->wpack_dirty || g->total_wpack == 0) { g->wpack_dirty = false; return 0; }
+  RC(sync_nets(g, st));
+  LAUNCH(launch_pack(g->d_nets.p, g->n_nets, g->d_params.p, g->d_wpack.p, st));
+  g->wpack_dirty = false;
+  return 0;
+}
+
+int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st) {
+  FitArgs a{};
+  a.nets = g->d_nets.p;
+  a.params = g->d_params.p;
+  a.axes = g->d_axes.p;
+  a.idx = reinterpret_cast<const long long*>(dev_idx);
+  a.seed = seed;
+  a.step = step;
+  a.partials = g->d_partials.p;
+  a.loss_partials = g->d_loss_partials.p;
+  a.wpack = g->d_wpack.p;
+  if (g->simt_fit.blocks > 0) {
+    a.work_prefix = g->d_fit_tables.p + g->simt_fit.off_prefix;
+    a.work_net = g->d_fit_tables.p + g->simt_fit.off_net;
+    a.n_work = g->simt_fit.n;
+    a.TM = g->simt_fit_tm;
+    LAUNCH(launch_simt_fit(a, g->simt_fit.blocks, g->simt_fit_smem, st));
+  }
+  for (int b = 1; b < kBuckets; ++b) {
+    if (g->tc_fit[b].blocks == 0) continue;
+    a.work_prefix = g->d_fit_tables.p + g->tc_fit[b].off_prefix;
+    a.work_net = g->d_fit_tables.p + g->tc_fit[b].off_net;
+    a.n_work = g->tc_fit[b].n;
+    a.TM = kTcTile;
+    LAUNCH(launch_tc_fit(a, 16 * b, g->tc_fit[b].blocks, st));
+  }
+  return 0;
+}
+
+int launch_opt_kernel(BriefGroup* g, bool from_partials, bool apply, int kind, double lr, double b1, double b2,
+                      double eps, long long t, float* loss_out, cudaStream_t st) {
+  OptArgs o{};
+  o.nets = g->d_nets.p;
+  o.blk_prefix = g->d_fit_tables.p + g->opt.off_prefix;
+  o.n_nets = g->n_nets;
+  o.params = g->d_params.p;
+  o.grads = g->d_grads.p;
+  o.m = g->d_m.p;
+  o.v = g->d_v.p;
+  o.partials = from_partials ? g->d_partials.p : nullptr;
+  o.loss_partials = g->d_loss_partials.p;
+  o.loss_out = loss_out;
+  o.kind = kind;
+  o.apply = apply ? 1 : 0;
+  if (apply) {
+    // torch: bias_correction = 1 - beta1 ** step ; clr = lr / bias_correction   (python doubles)
+    if (kind == BRIEF_OPT_SGD) {
+      o.neg_clr = (float)(-lr);
+    } else {
+      const double bc1 = 1.0 - std::pow(b1, (double)t);
+      o.neg_clr = (float)(-(lr / bc1));
+      o.w1 = (float)(1.0 - b1);
+      o.beta2 = (float)b2;
+      o.w2 = (float)(1.0 - b2);
+      o.eps = (float)eps;
+      o.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(b2, (double)t));
+    }
+  }
+  LAUNCH(launch_opt(o, g->opt.blocks, st));
+  if (apply) g->wpack_dirty = true;
+  return 0;
+}
+
+int check_bound(const BriefGroup* g) {
+  for (int i = 0; i < g->n_nets; ++i)
+    if (!g->nets[i].bound) return fail(BRIEF_ERR_STATE, "network %d has no volume bound (brief_group_bind_volume)", i);
+  return 0;
+}
+
+void linspace_host(float lo, float hi, int n, float* out) {
+  // torch CPU linspace, scalar form: step = (end-start)/(steps-1); first half from start, second from end
+  if (n == 1) { out[0] = lo; return; }
+  const float step = (hi - lo) / (float)(n - 1);
+  const int half = n / 2;
+  for (int i = 0; i < n; ++i) out[i] = i < half ? lo + step * (float)i : hi - step * (float)(n - i - 1);
+}
+
+}  // namespace
+
+extern "C" {
+
+int brief_abi_version(void) { return BRIEF_B200_ABI_VERSION; }
+const char* brief_last_error(void) { return g_err.c_str(); }
+int64_t brief_launch_count(void) { return g_launches.load(); }
+void brief_reset_launch_count(void) { g_launches.store(0); }
+
+int brief_device_count(int* out_count) {
+  if (!out_count) return fail(BRIEF_ERR_INVALID, "null out_count");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *out_count = 0;
+    return fail(BRIEF_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *out_count = n;
+  return 0;
+}
+
+int brief_linspace(float lo, float hi, int32_t n, float* host_out) {
+  if (n < 1 || !host_out) return fail(BRIEF_ERR_INVALID, "brief_linspace: n=%d", n);
+  linspace_host(lo, hi, n, host_out);
+  return 0;
+}
+
+int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device, int32_t precision,
+                       BriefGroup** out) {
+  if (!descs || n_nets < 1 || !out) return fail(BRIEF_ERR_INVALID, "brief_group_create: bad arguments");
+  if (precision < 0 || precision > 2) return fail(BRIEF_ERR_INVALID, "unknown precision %d", precision);
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(BRIEF_ERR_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  BriefGroup* g = new BriefGroup();
+  g->device = device;
+  g->n_nets = n_nets;
+  g->nets.resize(n_nets);
+  auto bail = [&](int rc) { brief_group_destroy(g); return rc; };
+  for (int i = 0; i < n_nets; ++i) {
+    const BriefNetDesc& d = descs[i];
+    if (d.coords_channel != 2 && d.coords_channel != 3)
+      return bail(fail(BRIEF_ERR_UNSUPPORTED, "net %d: coords_channel=%d (2 or 3 supported)", i, d.coords_channel));
+    if (d.data_channel != 1)
+      return bail(fail(BRIEF_ERR_UNSUPPORTED, "net %d: data_channel=%d (the fused kernels support 1)", i, d.data_channel));
+    if (d.features < 1 || d.layers < 2 || d.layers > BRIEF_MAX_LAYERS)
+      return bail(fail(BRIEF_ERR_INVALID, "net %d: features=%d layers=%d", i, d.features, d.layers));
+    if (d.dims[0] < 1 || d.dims[1] < 1 || d.dims[2] < 1 || (d.coords_channel == 2 && d.dims[0] != 1))
+      return bail(fail(BRIEF_ERR_INVALID, "net %d: dims=(%d,%d,%d)", i, d.dims[0], d.dims[1], d.dims[2]));
+    NetDev n{};
+    n.in_dim = d.coords_channel;
+    n.out_dim = d.data_channel;
+    n.f = d.features;
+    n.L = d.layers;
+    n.F4 = f4_of(d.features);
+    n.w0 = d.w0;
+    n.wh = d.w_hidden;
+    n.d = d.dims[0];
+    n.h = d.dims[1];
+    n.w = d.dims[2];
+    n.n_vox = (long long)n.d * n.h * n.w;
+    n.P_dev = dl_total(n.F4, n.L);
+    n.P_ref = n.in_dim * n.f + n.f + (n.L - 2) * (n.f * n.f + n.f) + n.f * n.out_dim + n.out_dim;
+    n.param_off = g->total_P;
+    g->total_P += n.P_dev;
+    n.axis_off = (int)g->total_axis;
+    g->total_axis += n.d + n.h + n.w;
+    if (g->total_axis > 0x7fffffffLL) return bail(fail(BRIEF_ERR_UNSUPPORTED, "axis table arena too large"));
+    const bool tc_ok = tc_supported(n.f, n.L, n.in_dim, n.out_dim);
+    if (precision == BRIEF_PREC_BF16 && !tc_ok)
+      return bail(fail(BRIEF_ERR_UNSUPPORTED,
+                       "net %d: features=%d layers=%d is outside the fused tcgen05 kernel's TMEM/SMEM budget; "
+                       "use BRIEF_PREC_FP32 or BRIEF_PREC_AUTO", i, n.f, n.L));
+    n.prec = (precision == BRIEF_PREC_FP32 || !tc_ok) ? BRIEF_PREC_FP32 : BRIEF_PREC_BF16;
+    if (n.prec == BRIEF_PREC_BF16) {
+      n.F_PAD = tc_fpad(n.f);
+      n.wpack_off = (long long)g->total_wpack;
+      g->total_wpack += (tc_wpack_bytes(n.F_PAD, n.L) + 127) & ~(size_t)127;
+    }
+    n.lo = 0.f; n.hi = 100.f; n.vmin = 0.f; n.vmax = 1.f;
+    n.dn_lo = 0.f; n.dn_hi = 100.f; n.dn_vmin = 0.f; n.dn_vmax = 1.f; n.dn_range = 1.f;
+    // main.py:332-334: whole-block sampling only for blocks of at most 80^3 voxels
+    n.mode = n.n_vox <= 80LL * 80 * 80 ? BRIEF_SAMPLE_FULL_BLOCK : BRIEF_SAMPLE_RANDOM_POINTS;
+    n.batch = n.mode == BRIEF_SAMPLE_FULL_BLOCK ? (int)n.n_vox : 100000;
+    g->nets[i] = n;
+  }
+  auto cu_bail = [&](cudaError_t e, const char* what) {
+    return bail(fail(BRIEF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e)));
+  };
+  cudaError_t e;
+  if ((e = g->d_nets.ensure(n_nets)) != cudaSuccess) return cu_bail(e, "alloc nets");
+  if ((e = g->d_params.ensure(g->total_P)) != cudaSuccess) return cu_bail(e, "alloc params");
+  if ((e = g->d_grads.ensure(g->total_P)) != cudaSuccess) return cu_bail(e, "alloc grads");
+  if ((e = g->d_m.ensure(g->total_P)) != cudaSuccess) return cu_bail(e, "alloc m");
+  if ((e = g->d_v.ensure(g->total_P)) != cudaSuccess) return cu_bail(e, "alloc v");
+  if ((e = g->d_axes.ensure(g->total_axis)) != cudaSuccess) return cu_bail(e, "alloc axes");
+  if ((e = g->d_wpack.ensure(g->total_wpack + 128)) != cudaSuccess) return cu_bail(e, "alloc wpack");
+  if ((e = g->d_outptrs.ensure(n_nets)) != cudaSuccess) return cu_bail(e, "alloc outptrs");
+  const size_t pb = (size_t)g->total_P * sizeof(float);
+  if ((e = cudaMemset(g->d_params.p, 0, pb)) != cudaSuccess) return cu_bail(e, "memset");
+  if ((e = cudaMemset(g->d_grads.p, 0, pb)) != cudaSuccess) return cu_bail(e, "memset");
+  if ((e = cudaMemset(g->d_m.p, 0, pb)) != cudaSuccess) return cu_bail(e, "memset");
+  if ((e = cudaMemset(g->d_v.p, 0, pb)) != cudaSuccess) return cu_bail(e, "memset");
+  if ((e = cudaMemset(g->d_wpack.p, 0, g->total_wpack + 128)) != cudaSuccess) return cu_bail(e, "memset");
+  std::vector<float> axes((size_t)g->total_axis);
+  for (auto& n : g->nets) {
+    linspace_host(-1.f, 1.f, n.d, axes.data() + n.axis_off);
+    linspace_host(-1.f, 1.f, n.h, axes.data() + n.axis_off + n.d);
+    linspace_host(-1.f, 1.f, n.w, axes.data() + n.axis_off + n.d + n.h);
+  }
+  if ((e = cudaMemcpy(g->d_axes.p, axes.data(), axes.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return cu_bail(e, "upload axes");
+  int rc = build_eval_tables(g, 0);
+  if (rc) return bail(rc);
+  *out = g;
+  return 0;
+}
+
+void brief_group_destroy(BriefGroup* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  g->d_nets.release(); g->d_params.release(); g->d_grads.release(); g->d_m.release(); g->d_v.release();
+  g->d_axes.release(); g->d_partials.release(); g->d_loss_partials.release(); g->d_loss_scratch.release();
+  g->d_wpack.release(); g->d_fit_tables.release(); g->d_eval_tables.release(); g->d_outptrs.release();
+  delete g;
+}
+
+int brief_group_num_nets(const BriefGroup* g) { return g ? g->n_nets : fail(BRIEF_ERR_INVALID, "null group"); }
+int brief_group_param_count(const BriefGroup* g, int32_t net) {
+  RC(check_net(g, net));
+  return g->nets[net].P_ref;
+}
+int brief_group_precision(const BriefGroup* g, int32_t net) {
+  RC(check_net(g, net));
+  return g->nets[net].prec;
+}
+
+static int arena_put(BriefGroup* g, int net, float* arena, const float* host_packed, cudaStream_t st) {
+  RC(check_net(g, net));
+  if (!host_packed) return fail(BRIEF_ERR_INVALID, "null host pointer");
+  RC(use_device(g));
+  const NetDev& n = g->nets[net];
+  std::vector<float> tmp(n.P_dev);
+  packed_to_dev(n, host_packed, tmp.data());
+  CU(cudaMemcpyAsync(arena + n.param_off, tmp.data(), sizeof(float) * n.P_dev, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+static int arena_get(BriefGroup* g, int net, const float* arena, float* host_packed, cudaStream_t st) {
+  RC(check_net(g, net));
+  if (!host_packed) return fail(BRIEF_ERR_INVALID, "null host pointer");
+  RC(use_device(g));
+  const NetDev& n = g->nets[net];
+  std::vector<float> tmp(n.P_dev);
+  CU(cudaMemcpyAsync(tmp.data(), arena + n.param_off, sizeof(float) * n.P_dev, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  dev_to_packed(n, tmp.data(), host_packed);
+  return 0;
+}
+
+int brief_group_set_params(BriefGroup* g, int32_t net, const float* host_packed, void* stream) {
+  RC(arena_put(g, net, g ? g->d_params.p : nullptr, host_packed, (cudaStream_t)stream));
+  g->wpack_dirty = true;
+  return 0;
+}
+int brief_group_get_params(BriefGroup* g, int32_t net, float* host_packed, void* stream) {
+  return arena_get(g, net, g ? g->d_params.p : nullptr, host_packed, (cudaStream_t)stream);
+}
+int brief_group_get_grads(BriefGroup* g, int32_t net, float* host_packed, void* stream) {
+  return arena_get(g, net, g ? g->d_grads.p : nullptr, host_packed, (cudaStream_t)stream);
+}
+int brief_group_set_grads(BriefGroup* g, int32_t net, const float* host_packed, void* stream) {
+  return arena_put(g, net, g ? g->d_grads.p : nullptr, host_packed, (cudaStream_t)stream);
+}
+int brief_group_get_opt_state(BriefGroup* g, int32_t net, float* host_m, float* host_v, void* stream) {
+  RC(arena_get(g, net, g ? g->d_m.p : nullptr, host_m, (cudaStream_t)stream));
+  return arena_get(g, net, g->d_v.p, host_v, (cudaStream_t)stream);
+}
+int brief_group_reset_opt_state(BriefGroup* g, void* stream) {
+  if (!g) return fail(BRIEF_ERR_INVALID, "null group");
+  RC(use_device(g));
+  CU(cudaMemsetAsync(g->d_m.p, 0, sizeof(float) * g->total_P, (cudaStream_t)stream));
+  CU(cudaMemsetAsync(g->d_v.p, 0, sizeof(float) * g->total_P, (cudaStream_t)stream));
+  return 0;
+}
+
+int brief_group_set_axes(BriefGroup* g, int32_t net, const float* host_d, const float* host_h, const float* host_w,
+                         void* stream) {
+  RC(check_net(g, net));
+  if (!host_d || !host_h || !host_w) return fail(BRIEF_ERR_INVALID, "null axis table");
+  RC(use_device(g));
+  const NetDev& n = g->nets[net];
+  std::vector<float> tmp((size_t)n.d + n.h + n.w);
+  std::copy(host_d, host_d + n.d, tmp.begin());
+  std::copy(host_h, host_h + n.h, tmp.begin() + n.d);
+  std::copy(host_w, host_w + n.w, tmp.begin() + n.d + n.h);
+  CU(cudaMemcpyAsync(g->d_axes.p + n.axis_off, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice,
+                     (cudaStream_t)stream));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int brief_group_bind_volume(BriefGroup* g, int32_t net, const void* dev_raw, int32_t dtype, float vmin, float vmax,
+                            float lo, float hi, const float* dev_weight, const BriefWeightRule* rules,
+                            int32_t n_rules, float tau) {
+  RC(check_net(g, net));
+  if (!dev_raw) return fail(BRIEF_ERR_INVALID, "null volume pointer");
+  if (dtype < 0 || dtype > 2) return fail(BRIEF_ERR_INVALID, "unknown dtype %d", dtype);
+  if (n_rules < 0 || n_rules > BRIEF_MAX_RULES) return fail(BRIEF_ERR_UNSUPPORTED, "at most %d weight rules", BRIEF_MAX_RULES);
+  if (n_rules > 0 && !rules) return fail(BRIEF_ERR_INVALID, "null rules");
+  NetDev& n = g->nets[net];
+  n.raw = dev_raw;
+  n.dtype = dtype;
+  n.weight = dev_weight;
+  n.vmin = vmin; n.vmax = vmax; n.lo = lo; n.hi = hi;
+  n.dn_vmin = vmin; n.dn_vmax = vmax; n.dn_lo = lo; n.dn_hi = hi;
+  n.dn_range = (float)((double)vmax - (double)vmin);
+  n.n_rules = n_rules;
+  for (int r = 0; r < n_rules; ++r) { n.rule_lo[r] = rules[r].lo; n.rule_hi[r] = rules[r].hi; n.rule_s[r] = rules[r].scale; }
+  n.tau = tau;
+  n.bound = 1;
+  g->nets_dirty = true;
+  return 0;
+}
+
+int brief_group_set_denorm(BriefGroup* g, int32_t net, float vmin, float vmax, float lo, float hi) {
+  RC(check_net(g, net));
+  NetDev& n = g->nets[net];
+  n.dn_vmin = vmin; n.dn_vmax = vmax; n.dn_lo = lo; n.dn_hi = hi;
+  n.dn_range = (float)((double)vmax - (double)vmin);
+  g->nets_dirty = true;
+  return 0;
+}
+
+int brief_group_set_sampler(BriefGroup* g, int32_t net, int32_t mode, int32_t batch) {
+  RC(check_net(g, net));
+  if (mode != BRIEF_SAMPLE_FULL_BLOCK && mode != BRIEF_SAMPLE_RANDOM_POINTS)
+    return fail(BRIEF_ERR_INVALID, "unknown sampler mode %d", mode);
+  if (mode == BRIEF_SAMPLE_RANDOM_POINTS && batch < 1) return fail(BRIEF_ERR_INVALID, "batch=%d", batch);
+  NetDev& n = g->nets[net];
+  n.mode = mode;
+  n.batch = mode == BRIEF_SAMPLE_FULL_BLOCK ? (int)std::min<long long>(n.n_vox, 0x7fffffffLL) : batch;
+  g->work_dirty = true;
+  g->nets_dirty = true;
+  return 0;
+}
+
+int brief_fit_step(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, float* dev_loss, void* stream) {
+  if (!g) return fail(BRIEF_ERR_INVALID, "null group");
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(check_bound(g));
+  RC(finalize(g, st));
+  RC(ensure_wpack(g, st));
+  RC(launch_fit_kernels(g, dev_idx, seed, step, st));
+  return launch_opt_kernel(g, true, false, 0, 0, 0, 0, 0, 0, dev_loss ? dev_loss : g->d_loss_scratch.p, st);
+}
+
+int brief_opt_step(BriefGroup* g, int32_t kind, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {
+  if (!g) return fail(BRIEF_ERR_INVALID, "null group");
+  if (kind < 0 || kind > 2) return fail(BRIEF_ERR_INVALID, "unknown optimiser %d", kind);
+  if (t < 1) return fail(BRIEF_ERR_INVALID, "optimiser step count t=%lld must be >= 1", (long long)t);
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(finalize(g, st));
+  return launch_opt_kernel(g, false, true, kind, lr, beta1, beta2, eps, t, nullptr, st);
+}
+
+int brief_fit_run(BriefGroup* g, const BriefOptConfig* cfg, uint64_t seed, int64_t steps_done, int64_t n_steps,
+                  float* dev_loss_hist, void* stream) {
+  if (!g || !cfg) return fail(BRIEF_ERR_INVALID, "null argument");
+  if (cfg->kind < 0 || cfg->kind > 2) return fail(BRIEF_ERR_INVALID, "unknown optimiser %d", cfg->kind);
+  if (cfg->n_milestones < 0 || cfg->n_milestones > 8) return fail(BRIEF_ERR_INVALID, "n_milestones=%d", cfg->n_milestones);
+  if (steps_done < 0 || n_steps < 0) return fail(BRIEF_ERR_INVALID, "negative step count");
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(check_bound(g));
+  RC(finalize(g, st));
+  for (int64_t s = 0; s < n_steps; ++s) {
+    const int64_t t = steps_done + s + 1;  // 1-based optimiser step
+    // MultiStepLR (utils/misc.py:187-188): scheduler.step() runs after optimizer.step(), so step t uses
+    // lr0 * gamma^(#milestones <= t-1), accumulated by chained double multiplications like torch.
+    double lr = cfg->lr;
+    for (int i = 0; i < cfg->n_milestones; ++i)
+      if (cfg->milestones[i] <= t - 1) lr *= (double)cfg->gamma;
+    RC(ensure_wpack(g, st));
+    RC(launch_fit_kernels(g, nullptr, seed, (uint64_t)(t - 1), st));
+    float* loss_out = dev_loss_hist ? dev_loss_hist + (size_t)s * g->n_nets : g->d_loss_scratch.p;
+    RC(launch_opt_kernel(g, true, true, cfg->kind, lr, cfg->beta1, cfg->beta2, cfg->eps, t, loss_out, st));
+  }
+  return 0;
+}
+
+int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n, float* dev_out, float* dev_layers,
+                  void* stream) {
+  RC(check_net(g, net));
+  if (!dev_coords || !dev_out || n < 0) return fail(BRIEF_ERR_INVALID, "brief_forward: bad arguments");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(sync_nets(g, st));
+  const NetDev& nd = g->nets[net];
+  EvalArgs a{};
+  a.nets = g->d_nets.p;
+  a.params = g->d_params.p;
+  a.axes = g->d_axes.p;
+  a.single_net = net;
+  a.coords = dev_coords;
+  a.n_coords = n;
+  a.out_f32 = dev_out;
+  a.layers_out = dev_layers;
+  a.wpack = g->d_wpack.p;
+  if (nd.prec == BRIEF_PREC_BF16) {
+    RC(ensure_wpack(g, st));
+    const long long tiles = (n + kTcTile - 1) / kTcTile;
+    const long long blocks = (tiles + kTcEvalTilesPerBlock - 1) / kTcEvalTilesPerBlock;
+    a.TM = kTcTile;
+    LAUNCH(launch_tc_eval(a, nd.F_PAD, (int)blocks, st));
+  } else {
+    const int tm = simt_pick_tm(nd.F4, nd.L, false, kSmemLimit);
+    if (tm == 0) return fail(BRIEF_ERR_UNSUPPORTED, "features=%d exceed the fp32 kernel's shared-memory budget", nd.f);
+    a.TM = tm;
+    const long long tiles = (n + tm - 1) / tm;
+    if (tiles > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "too many coordinates for one launch");
+    LAUNCH(launch_simt_eval(a, (int)tiles, simt_eval_smem(nd.F4, tm), st));
+  }
+  return 0;
+}
+
+int brief_decompress(BriefGroup* g, void* const* host_dev_out, int32_t out_dtype, void* stream) {
+  if (!g || !host_dev_out) return fail(BRIEF_ERR_INVALID, "null argument");
+  if (out_dtype < 0 || out_dtype > 2) return fail(BRIEF_ERR_INVALID, "unknown dtype %d", out_dtype);
+  for (int i = 0; i < g->n_nets; ++i)
+    if (!host_dev_out[i]) return fail(BRIEF_ERR_INVALID, "null destination for network %d", i);
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(sync_nets(g, st));
+  CU(cudaMemcpyAsync(g->d_outptrs.p, host_dev_out, sizeof(void*) * g->n_nets, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  EvalArgs a{};
+  a.nets = g->d_nets.p;
+  a.params = g->d_params.p;
+  a.axes = g->d_axes.p;
+  a.single_net = -1;
+  a.out_ptrs = g->d_outptrs.p;
+  a.out_dtype = out_dtype;
+  a.wpack = g->d_wpack.p;
+  if (g->simt_eval.blocks > 0) {
+    a.work_prefix = g->d_eval_tables.p + g->simt_eval.off_prefix;
+    a.work_net = g->d_eval_tables.p + g->simt_eval.off_net;
+    a.n_work = g->simt_eval.n;
+    a.TM = g->simt_eval_tm;
+    LAUNCH(launch_simt_eval(a, g->simt_eval.blocks, g->simt_eval_smem, st));
+  }
+  bool packed = false;
+  for (int b = 1; b < kBuckets; ++b) {
+    if (g->tc_eval[b].blocks == 0) continue;
+    if (!packed) { RC(ensure_wpack(g, st)); packed = true; }
+    a.work_prefix = g->d_eval_tables.p + g->tc_eval[b].off_prefix;
+    a.work_net = g->d_eval_tables.p + g->tc_eval[b].off_net;
+    a.n_work = g->tc_eval[b].n;
+    a.TM = kTcTile;
+    LAUNCH(launch_tc_eval(a, 16 * b, g->tc_eval[b].blocks, st));
+  }
+  return 0;
+}
+
+int brief_gather(BriefGroup* g, int32_t net, const int64_t* dev_idx, int64_t batch, float* dev_coords, float* dev_data,
+                 float* dev_weight, void* stream) {
+  RC(check_net(g, net));
+  if (batch < 0) return fail(BRIEF_ERR_INVALID, "batch=%lld", (long long)batch);
+  if (!g->nets[net].bound && (dev_data || dev_weight)) return fail(BRIEF_ERR_STATE, "network %d has no volume bound", net);
+  if (batch == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(sync_nets(g, st));
+  LAUNCH(launch_gather(g->d_nets.p, net, g->d_axes.p, reinterpret_cast<const long long*>(dev_idx), batch, dev_coords,
+                       dev_data, dev_weight, st));
+  return 0;
+}
+
+int brief_sample_indices(uint64_t seed, uint64_t step, int32_t net, int64_t batch, int64_t pop, int64_t* dev_out,
+                         void* stream) {
+  if (!dev_out || batch < 0 || pop < 1 || pop > 0xffffffffLL) return fail(BRIEF_ERR_INVALID, "brief_sample_indices: bad arguments");
+  if (batch == 0) return 0;
+  LAUNCH(launch_sample_indices(seed, step, (uint32_t)net, batch, pop, reinterpret_cast<long long*>(dev_out),
+                               (cudaStream_t)stream));
+  return 0;
+}
+
+}  // extern "C"

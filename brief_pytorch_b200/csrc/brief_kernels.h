@@ -1,0 +1,97 @@
+// brief_kernels.h — kernel argument blocks and host launchers shared between the translation
+// units of libbrief_b200 (brief_simt.cu, brief_tc.cu, brief_opt.cu, brief_capi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "brief_common.cuh"
+
+namespace brief {
+
+// Forward / decompress work: block b serves tile (b - work_prefix[i]) of network work_net[i].
+struct EvalArgs {
+  const NetDev* nets;
+  const float* params;
+  const float* axes;
+  const int* work_prefix;  // n_work + 1 entries (tiles, exclusive prefix sum)
+  const int* work_net;     // n_work entries, or NULL for identity
+  int n_work;
+  int single_net;          // >= 0: one network, block b = tile b (work tables unused)
+  int TM;
+  // explicit-coordinate mode (brief_forward); NULL = dense grid of the network's block
+  const float* coords;
+  long long n_coords;
+  float* out_f32;      // explicit mode destination
+  float* layers_out;   // optional z_l dump [L-1][n][f]
+  // dense mode destinations
+  void* const* out_ptrs;  // device array indexed by network id
+  int out_dtype;
+  // tensor-core path only
+  const unsigned char* wpack;
+};
+
+// Fit work: block b serves slice (b - work_prefix[i]) of network work_net[i].
+struct FitArgs {
+  const NetDev* nets;
+  const float* params;
+  const float* axes;
+  const int* work_prefix;
+  const int* work_net;
+  int n_work;
+  int TM;
+  const long long* idx;  // replayed sampler indices or NULL
+  uint64_t seed, step;
+  float* partials;       // per-slice gradient slots (padded device layout)
+  float* loss_partials;  // per-slice loss terms
+  const unsigned char* wpack;
+};
+
+// Optimiser step over the whole group (one launch).
+struct OptArgs {
+  const NetDev* nets;
+  const int* blk_prefix;  // n_nets + 1: blocks per network (256 params each)
+  int n_nets;
+  float* params;
+  float* grads;
+  float* m;
+  float* v;
+  const float* partials;       // NULL: consume `grads`; else reduce slices in order first
+  const float* loss_partials;  // with partials: per-network loss = ordered sum
+  float* loss_out;             // n_nets floats or NULL
+  int kind;
+  float neg_clr;     // -(lr / (1 - beta1^t))   [Adamax/Adam] or -lr [SGD]
+  float w1;          // 1 - beta1   (lerp weight)
+  float beta2;
+  float w2;          // 1 - beta2   (Adam addcmul value)
+  float eps;
+  float bc2_sqrt;    // sqrt(1 - beta2^t) (Adam)
+  int apply;         // 0 = only reduce partials into grads / loss (brief_fit_step)
+  unsigned char* wpack;  // refreshed bf16 operand image (tensor-core networks) or NULL
+};
+
+// brief_simt.cu
+int simt_pick_tm(int F4, int L, bool fit, size_t smem_limit);
+size_t simt_eval_smem(int F4, int TM);
+size_t simt_fit_smem(int F4, int L, int TM);
+cudaError_t launch_simt_eval(const EvalArgs& a, int n_blocks, size_t smem, cudaStream_t st);
+cudaError_t launch_simt_fit(const FitArgs& a, int n_blocks, size_t smem, cudaStream_t st);
+cudaError_t launch_gather(const NetDev* nets, int net_id, const float* axes, const long long* idx, long long batch,
+                          float* coords, float* data, float* weight, cudaStream_t st);
+cudaError_t launch_sample_indices(uint64_t seed, uint64_t step, uint32_t net, long long batch, long long pop,
+                                  long long* out, cudaStream_t st);
+
+// brief_opt.cu
+cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st);
+cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, unsigned char* wpack, cudaStream_t st);
+
+// brief_tc.cu (tcgen05 path)
+bool tc_supported(int f, int L, int in_dim, int out_dim);
+int tc_fpad(int f);
+size_t tc_wpack_bytes(int F_PAD, int L);
+size_t tc_eval_smem(int F_PAD, int L);
+size_t tc_fit_smem(int F_PAD, int L);
+cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int n_blocks, cudaStream_t st);
+cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int n_blocks, cudaStream_t st);
+
+}  // namespace brief

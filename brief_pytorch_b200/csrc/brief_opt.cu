@@ -1,0 +1,139 @@
+// brief_opt.cu — per-network fused optimiser step for the whole group in ONE launch, plus the
+// refresh of the bf16 operand image used by the tcgen05 kernels.
+//
+// Reference work replaced: torch.optim.Adamax / Adam / SGD .step() (configure_optimizer,
+// utils/misc.py:174-183; main.py:399) — ~6 tiny ATen ops x 2L tensors per network per step — and
+// optimizer.zero_grad() (main.py:387; gradients here are written, never accumulated).
+//
+// The arithmetic follows torch's single-tensor CPU kernels operation by operation:
+//   Adamax : m = fma(1-b1, g-m, m)          (lerp_, vectorised form)
+//            u = max(u*b2, |g|+eps)
+//            p = p + ((-clr*m)/u)           (addcdiv_, clr = lr/(1-b1^t) computed in double on the host)
+//   Adam   : m as above;  v = v*b2 + ((1-b2)*g)*g ;  den = sqrt(v)/sqrt(1-b2^t) + eps ;  p = p + ((-clr*m)/den)
+//   SGD    : p = fma(-lr, g, p)
+// When `partials` is given the kernel first reduces the per-slice gradient slots IN SLICE ORDER
+// (deterministic, independent of how many networks share the GPU) — 28 B/param of optimiser traffic
+// plus 4 B/param/slice of partial traffic; HBM/L2-bound and tiny next to the fit kernel.
+#include "brief_common.cuh"
+#include "brief_kernels.h"
+#include <cuda_bf16.h>
+
+namespace brief {
+
+constexpr int kOptThreads = 256;
+
+__global__ void __launch_bounds__(kOptThreads) opt_kernel(OptArgs a) {
+  // locate network: blk_prefix has n_nets+1 entries
+  int lo = 0, hi = a.n_nets;
+  const int b = blockIdx.x;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a.blk_prefix + mid) <= b) lo = mid; else hi = mid;
+  }
+  const NetDev& n = a.nets[lo];
+  const int blk = b - a.blk_prefix[lo];
+  const int i = blk * kOptThreads + threadIdx.x;
+
+  // per-network loss: ordered reduction of the slice partials by warp 0 of the network's first block
+  if (blk == 0 && threadIdx.x < 32 && a.partials && a.loss_out) {
+    float acc = 0.f;
+    for (int s = threadIdx.x; s < n.n_slices; s += 32) acc += a.loss_partials[n.slice_off + s];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+    if (threadIdx.x == 0) a.loss_out[lo] = acc;
+  }
+  if (i >= n.P_dev) return;
+  const long long gi = n.param_off + i;
+  float g;
+  if (a.partials) {
+    const float* src = a.partials + n.part_off + i;
+    g = 0.f;
+    int s = 0;
+    for (; s + 4 <= n.n_slices; s += 4) {
+      const float g0 = src[(long long)(s + 0) * n.P_dev], g1 = src[(long long)(s + 1) * n.P_dev];
+      const float g2 = src[(long long)(s + 2) * n.P_dev], g3 = src[(long long)(s + 3) * n.P_dev];
+      g = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(g, g0), g1), g2), g3);
+    }
+    for (; s < n.n_slices; ++s) g = __fadd_rn(g, src[(long long)s * n.P_dev]);
+    a.grads[gi] = g;
+  } else {
+    g = a.grads[gi];
+  }
+  if (!a.apply) return;
+  float p = a.params[gi];
+  if (a.kind == 2) {  // SGD: param.add_(grad, alpha=-lr)
+    p = fmaf(a.neg_clr, g, p);
+  } else {
+    float m = a.m[gi], v = a.v[gi];
+    m = fmaf(a.w1, __fsub_rn(g, m), m);
+    float den;
+    if (a.kind == 0) {  // Adamax
+      v = fmaxf(__fmul_rn(v, a.beta2), __fadd_rn(fabsf(g), a.eps));
+      den = v;
+    } else {  // Adam
+      v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(a.w2, g), g));
+      den = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.bc2_sqrt), a.eps);
+    }
+    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(a.neg_clr, m), den));
+    a.m[gi] = m;
+    a.v[gi] = v;
+  }
+  a.params[gi] = p;
+}
+
+cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st) {
+  opt_kernel<<<n_blocks, kOptThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ---- bf16 operand image for the tcgen05 kernels ----------------------------------------------------
+// Image of network n (bytes, at wpack + n.wpack_off), F = F_PAD, NH = L-2:
+//   [NH] hidden weights, bf16, UMMA no-swizzle core-matrix layout: element (o,k) of layer l at
+//        l*F*F*2 + ((k/8)*(F/8) + o/8)*128 + (o%8)*16 + (k%8)*2       (8x8 cores, K contiguous)
+//   then fp32: first layer float4 (wx,wy,wz,b0) x F | omega*bias [NH][F] | Wlast [F] | blast,0,0,0
+__global__ void pack_kernel(const NetDev* nets, int n_nets, const float* __restrict__ params, unsigned char* wpack) {
+  for (int net_id = blockIdx.y; net_id < n_nets; net_id += gridDim.y) {
+  const NetDev& n = nets[net_id];
+  if (n.prec != 1) continue;
+  const int F = n.F_PAD, NH = n.L - 2, f = n.f, F4 = n.F4;
+  const float* P = params + n.param_off;
+  unsigned char* img = wpack + n.wpack_off;
+  const int n_hidden = NH * F * F;
+  const int n_side = 4 * F + NH * F + F + 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hidden + n_side; i += gridDim.x * blockDim.x) {
+    if (i < n_hidden) {
+      const int l = i / (F * F), r = i - l * F * F;
+      const int o = r / F, k = r - o * F;
+      const float w = (o < f && k < f) ? P[dl_W(n, l + 1) + o * F4 + k] : 0.f;
+      const size_t off = (size_t)l * F * F * 2 + ((size_t)(k >> 3) * (F >> 3) + (o >> 3)) * 128 + (o & 7) * 16 + (k & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(w);
+    } else {
+      const int j = i - n_hidden;
+      float* side = reinterpret_cast<float*>(img + (size_t)n_hidden * 2);
+      float val;
+      if (j < 4 * F) {
+        const int o = j >> 2, c = j & 3;
+        val = (o < f) ? (c < 3 ? P[dl_W0(n) + 4 * o + c] : P[dl_b0(n) + o]) : 0.f;
+      } else if (j < 4 * F + NH * F) {
+        const int q = j - 4 * F, l = q / F, o = q - l * F;
+        val = (o < f) ? __fmul_rn(n.wh, P[dl_b(n, l + 1) + o]) : 0.f;
+      } else if (j < 4 * F + NH * F + F) {
+        const int k = j - 4 * F - NH * F;
+        val = (k < f) ? P[dl_Wlast(n) + k] : 0.f;
+      } else {
+        const int c = j - (4 * F + NH * F + F);
+        val = c == 0 ? P[dl_blast(n)] : 0.f;
+      }
+      side[j] = val;
+    }
+  }
+  }
+}
+
+cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, unsigned char* wpack, cudaStream_t st) {
+  dim3 grid(8, n_nets < 32768 ? n_nets : 32768);
+  pack_kernel<<<grid, 256, 0, st>>>(nets, n_nets, params, wpack);
+  return cudaGetLastError();
+}
+
+}  // namespace brief

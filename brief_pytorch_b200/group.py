@@ -1,0 +1,277 @@
+"""SirenGroup — Python handle on a BriefGroup (include/brief_b200.h): many independent per-block SIREN
+networks fitted / evaluated together by grouped sm_100a kernel launches.
+
+Replaces the reference's per-block process farm (main.py:547-579, utils/TasksManager.py) and the
+per-step Python loop of main.py:385-400.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import (DT_F32, DT_U16, DT_U8, OPT_ADAM, OPT_ADAMAX, OPT_SGD, PREC_AUTO, PREC_BF16, PREC_FP32,
+                    SAMPLE_FULL_BLOCK, SAMPLE_RANDOM_POINTS, check)
+
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16, "auto": PREC_AUTO}
+_OPT = {"Adamax": OPT_ADAMAX, "Adam": OPT_ADAM, "SGD": OPT_SGD}
+_NP2DT = {"uint8": DT_U8, "uint16": DT_U16, "float32": DT_F32}
+_DT2TORCH = {DT_U8: torch.uint8, DT_U16: torch.int16, DT_F32: torch.float32}  # u16 held as int16 bit patterns
+
+
+@dataclass
+class NetSpec:
+    """Architecture + block geometry of one network (SIREN kwargs, utils/Networks.py:246)."""
+    features: int
+    layers: int
+    w0: float
+    dims: Sequence[int]            # (d,h,w) or (h,w)
+    coords_channel: int = 3
+    data_channel: int = 1
+    w_hidden: float = 30.0
+
+    def param_count(self) -> int:
+        c, o, f, L = self.coords_channel, self.data_channel, self.features, self.layers
+        return c * f + f + (L - 2) * (f * f + f) + f * o + o
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def pack_module_params(module) -> np.ndarray:
+    """Flatten a SIREN-like module (`.net[l][0].weight/.bias`) in the order utils/ModelSave.py writes."""
+    parts = []
+    for l in range(len(module.net)):
+        parts.append(module.net[l][0].weight.detach().to("cpu", torch.float32).reshape(-1).numpy())
+        parts.append(module.net[l][0].bias.detach().to("cpu", torch.float32).reshape(-1).numpy())
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+def unpack_module_params(module, flat: np.ndarray) -> None:
+    off = 0
+    with torch.no_grad():
+        for l in range(len(module.net)):
+            lin = module.net[l][0]
+            for p in (lin.weight, lin.bias):
+                n = p.numel()
+                p.data = torch.from_numpy(flat[off:off + n].reshape(tuple(p.shape)).copy()).to(p.device, p.dtype)
+                off += n
+    assert off == flat.size
+
+
+class SirenGroup:
+    def __init__(self, specs: Sequence[NetSpec], device: int | str | torch.device = 0, precision: str = "auto"):
+        self._lib = _cabi.load()
+        self._h = C.c_void_p()
+        if not torch.cuda.is_available():
+            raise _cabi.BriefError(-2, "no CUDA device: brief_pytorch_b200 has no CPU path")
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.specs = list(specs)
+        descs = (_cabi.NetDesc * len(self.specs))()
+        for i, s in enumerate(self.specs):
+            dims = tuple(int(x) for x in s.dims)
+            if len(dims) == 2:
+                dims = (1,) + dims
+            descs[i] = _cabi.NetDesc(s.coords_channel, s.data_channel, s.features, s.layers, float(s.w0),
+                                     float(s.w_hidden), (C.c_int32 * 3)(*dims))
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream()  # make sure the primary context exists
+            check(self._lib.brief_group_create(descs, len(self.specs), idx, _PREC[precision], C.byref(self._h)))
+        self._keep: Dict[int, tuple] = {}  # tensors bound to the group must outlive it
+        self.steps_done = 0
+
+    # ---- life cycle -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.brief_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return len(self.specs)
+
+    def precision(self, net: int) -> str:
+        return {PREC_FP32: "fp32", PREC_BF16: "bf16"}[check(self._lib.brief_group_precision(self._h, net))]
+
+    def param_count(self, net: int) -> int:
+        return check(self._lib.brief_group_param_count(self._h, net))
+
+    # ---- parameters ---------------------------------------------------------------------------------
+    def set_params(self, net: int, flat: np.ndarray) -> None:
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.size == self.param_count(net), (flat.size, self.param_count(net))
+        check(self._lib.brief_group_set_params(self._h, net, flat.ctypes.data_as(C.c_void_p), _stream(self.device)))
+
+    def _get(self, fn, net: int) -> np.ndarray:
+        out = np.empty(self.param_count(net), dtype=np.float32)
+        check(fn(self._h, net, out.ctypes.data_as(C.c_void_p), _stream(self.device)))
+        return out
+
+    def get_params(self, net: int) -> np.ndarray:
+        return self._get(self._lib.brief_group_get_params, net)
+
+    def get_grads(self, net: int) -> np.ndarray:
+        return self._get(self._lib.brief_group_get_grads, net)
+
+    def set_grads(self, net: int, flat: np.ndarray) -> None:
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.size == self.param_count(net)
+        check(self._lib.brief_group_set_grads(self._h, net, flat.ctypes.data_as(C.c_void_p), _stream(self.device)))
+
+    def get_opt_state(self, net: int):
+        m = np.empty(self.param_count(net), dtype=np.float32)
+        v = np.empty_like(m)
+        check(self._lib.brief_group_get_opt_state(self._h, net, m.ctypes.data_as(C.c_void_p),
+                                                  v.ctypes.data_as(C.c_void_p), _stream(self.device)))
+        return m, v
+
+    def reset_opt_state(self) -> None:
+        check(self._lib.brief_group_reset_opt_state(self._h, _stream(self.device)))
+        self.steps_done = 0
+
+    def load_module(self, net: int, module) -> None:
+        self.set_params(net, pack_module_params(module))
+
+    def store_module(self, net: int, module) -> None:
+        unpack_module_params(module, self.get_params(net))
+
+    def set_axes(self, net: int, coords_mode: str = "-1,1") -> None:
+        """Per-axis tables from torch.linspace on the CPU — bit-identical to the reference's create_coords."""
+        from .dataset import axis_table
+        s = self.specs[net]
+        dims = tuple(int(x) for x in s.dims)
+        if len(dims) == 2:
+            dims = (1,) + dims
+        tabs = [np.ascontiguousarray(axis_table(n, coords_mode).numpy(), dtype=np.float32) for n in dims]
+        check(self._lib.brief_group_set_axes(self._h, net, *[t.ctypes.data_as(C.c_void_p) for t in tabs],
+                                             _stream(self.device)))
+
+    # ---- data -------------------------------------------------------------------------------------------
+    def bind_volume(self, net: int, raw: torch.Tensor, vmin: float, vmax: float, lo: float = 0.0, hi: float = 100.0,
+                    weight: Optional[torch.Tensor] = None, rules: Sequence[Sequence[float]] = (), tau: float = 0.0,
+                    np_dtype: Optional[str] = None) -> None:
+        """raw: CUDA tensor with the block's voxels in d,h,w order (uint8 / int16-viewed uint16 / float32)."""
+        assert raw.is_cuda and raw.is_contiguous()
+        s = self.specs[net]
+        assert raw.numel() == int(np.prod(s.dims)), (raw.shape, s.dims)
+        if np_dtype is None:
+            np_dtype = {torch.uint8: "uint8", torch.int16: "uint16", torch.float32: "float32"}[raw.dtype]
+        if hasattr(torch, "uint16") and raw.dtype == getattr(torch, "uint16"):
+            np_dtype = "uint16"
+        if weight is not None:
+            assert weight.is_cuda and weight.dtype == torch.float32 and weight.is_contiguous()
+            assert weight.numel() == raw.numel()
+        if len(rules) > _cabi.MAX_WEIGHT_RULES:
+            raise NotImplementedError("more than 4 value rules: pass an explicit weight volume")
+        arr = (_cabi.WeightRule * max(1, len(rules)))()
+        for i, r in enumerate(rules):
+            arr[i] = _cabi.WeightRule(float(r[0]), float(r[1]), float(r[2]))
+        check(self._lib.brief_group_bind_volume(self._h, net, _ptr(raw), _NP2DT[np_dtype], float(vmin), float(vmax),
+                                                float(lo), float(hi), _ptr(weight), arr, len(rules), float(tau)))
+        self._keep[net] = (raw, weight)
+
+    def set_denorm(self, net: int, vmin: float, vmax: float, lo: float = 0.0, hi: float = 100.0) -> None:
+        check(self._lib.brief_group_set_denorm(self._h, net, float(vmin), float(vmax), float(lo), float(hi)))
+
+    def set_sampler(self, net: int, mode: str, batch: int = 0) -> None:
+        m = {"randomcube": SAMPLE_FULL_BLOCK, "full": SAMPLE_FULL_BLOCK, "randompoint": SAMPLE_RANDOM_POINTS}[mode]
+        check(self._lib.brief_group_set_sampler(self._h, net, m, int(batch)))
+
+    # ---- hot path -----------------------------------------------------------------------------------------
+    def fit_step(self, idx: Optional[torch.Tensor] = None, seed: int = 0, step: int = 0) -> torch.Tensor:
+        """gather + forward + weighted L2 + backward for every network; returns the per-network loss."""
+        loss = torch.empty(len(self.specs), dtype=torch.float32, device=self.device)
+        if idx is not None:
+            assert idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_fit_step(self._h, _ptr(idx), seed, step, _ptr(loss), _stream(self.device)))
+        return loss
+
+    def opt_step(self, kind: str = "Adamax", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 t: Optional[int] = None) -> None:
+        if t is None:
+            t = self.steps_done + 1
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_opt_step(self._h, _OPT[kind], lr, betas[0], betas[1], eps, t, _stream(self.device)))
+        self.steps_done = t
+
+    def fit_run(self, n_steps: int, kind: str = "Adamax", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                milestones: Sequence[int] = (), gamma: float = 0.2, seed: int = 42,
+                loss_history: bool = False) -> Optional[torch.Tensor]:
+        """n_steps iterations of main.py:385-400 enqueued from C without host synchronisation."""
+        cfg = _cabi.OptConfig(_OPT[kind], lr, betas[0], betas[1], eps, len(milestones),
+                              (C.c_int64 * 8)(*list(milestones)[:8]), gamma)
+        hist = torch.empty((n_steps, len(self.specs)), dtype=torch.float32, device=self.device) if loss_history else None
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_fit_run(self._h, C.byref(cfg), seed, self.steps_done, n_steps, _ptr(hist),
+                                          _stream(self.device)))
+        self.steps_done += n_steps
+        return hist
+
+    def forward(self, net: int, coords: torch.Tensor, return_layers: bool = False):
+        """SIREN.forward on explicit coordinates [..., coords_channel] -> [..., 1] (fp32, CUDA)."""
+        s = self.specs[net]
+        assert coords.is_cuda and coords.dtype == torch.float32
+        flat = coords.reshape(-1, s.coords_channel).contiguous()
+        n = flat.shape[0]
+        out = torch.empty((n, 1), dtype=torch.float32, device=self.device)
+        layers = torch.zeros((s.layers - 1, n, s.features), dtype=torch.float32, device=self.device) if return_layers else None
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_forward(self._h, net, _ptr(flat), n, _ptr(out), _ptr(layers), _stream(self.device)))
+        out = out.reshape(*coords.shape[:-1], 1)
+        return (out, layers) if return_layers else out
+
+    def decompress(self, out_dtype: str = "uint16", out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """Dense-grid evaluation + inverse normalisation + truncating cast for every network (one launch
+        per kernel family).  Returns one tensor per network shaped like its block (uint16 as int16 bits)."""
+        dt = _NP2DT[out_dtype]
+        if out is None:
+            out = [torch.empty(tuple(int(x) for x in s.dims), dtype=_DT2TORCH[dt], device=self.device) for s in self.specs]
+        ptrs = (C.c_void_p * len(out))(*[t.data_ptr() for t in out])
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_decompress(self._h, ptrs, dt, _stream(self.device)))
+        return out
+
+    def gather(self, net: int, idx: Optional[torch.Tensor], batch: Optional[int] = None):
+        """The reference sampler's (coords, data, weight) for the given voxel indices (main.py:156-160)."""
+        s = self.specs[net]
+        n = int(idx.numel()) if idx is not None else int(batch)
+        coords = torch.empty((n, s.coords_channel), dtype=torch.float32, device=self.device)
+        data = torch.empty((n, 1), dtype=torch.float32, device=self.device)
+        weight = torch.empty((n, 1), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_gather(self._h, net, _ptr(idx), n, _ptr(coords), _ptr(data), _ptr(weight),
+                                         _stream(self.device)))
+        return coords, data, weight
+
+
+def sample_indices(seed: int, step: int, net: int, batch: int, pop: int, device="cuda") -> torch.Tensor:
+    """Index stream of the on-device sampler (Philox4x32-10), int64 [batch]."""
+    lib = _cabi.load()
+    out = torch.empty(batch, dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        check(lib.brief_sample_indices(seed, step, net, batch, pop, _ptr(out), _stream(out.device)))
+    return out
+
+
+def launch_count() -> int:
+    return int(_cabi.load().brief_launch_count())
+
+
+def reset_launch_count() -> None:
+    _cabi.load().brief_reset_launch_count()

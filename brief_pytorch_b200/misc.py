@@ -1,0 +1,289 @@
+"""Host-side helpers with the reference's signatures (utils/misc.py): checkpoints, loss weights, optimiser /
+scheduler configuration, dense reconstruction, block partition and merge, quality metrics."""
+from __future__ import annotations
+
+import copy
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Iterable, List, Sequence
+
+import numpy as np
+import torch
+
+from .dataset import create_flattened_coords
+from .io import get_type_max
+
+
+# ---- checkpoints / weights ------------------------------------------------------------------------------
+def parse_checkpoints(checkpoints, max_steps: int) -> List[int]:
+    """'none' | 'every_N' | 'a,b,c' -> sorted step list that always ends with max_steps (utils/misc.py:255-271;
+    like the reference, a bare int is rejected by the 'every' membership test with TypeError)."""
+    if checkpoints == "none":
+        return [max_steps]
+    if "every" in checkpoints:
+        every = int(checkpoints.split("_")[1])
+        return list(range(every, max_steps, every)) + [max_steps]
+    return [int(tok) for tok in checkpoints.split(",") if int(tok) < max_steps] + [max_steps]
+
+
+def _limits(data: np.ndarray, lo: float, hi: float):
+    if not (0 <= lo <= hi <= get_type_max(data)):
+        raise AssertionError("Improper range setting!")
+    return lo, hi
+
+
+def parse_weight(data: np.ndarray, weight_type_list: Iterable[str]) -> np.ndarray:
+    """Per-voxel loss weights from the rule strings of Compress.loss.weight (utils/misc.py:272-307)."""
+    data = np.asarray(data)
+    weight = np.ones(data.shape, dtype=np.float32)
+    for rule in weight_type_list:
+        if rule == "none":
+            continue
+        kind, *args = rule.split("_")
+        vals = [float(a) for a in args]
+        if kind == "value":
+            lo, hi = _limits(data, vals[0], vals[1])
+            weight[(data >= lo) & (data <= hi)] = vals[2]
+        elif kind == "quantile":
+            sel = data[data >= vals[0]]
+            lo, hi = _limits(data, np.quantile(sel, vals[1]), np.quantile(sel, vals[2]))
+            weight[(data >= lo) & (data <= hi)] = vals[3]
+        elif kind == "exp":
+            weight = np.exp(-(-np.log(vals[1]) / vals[0]) * data)
+        else:
+            raise NotImplementedError(rule)
+    return weight
+
+
+def weight_rules_for_kernel(data: np.ndarray, weight_type_list: Iterable[str]):
+    """Translate rule strings into on-chip (lo, hi, scale) triples; returns None when a rule needs the
+    explicit weight volume ('exp', or more than 4 rules)."""
+    rules = []
+    for rule in weight_type_list:
+        if rule == "none":
+            continue
+        kind, *args = rule.split("_")
+        vals = [float(a) for a in args]
+        if kind == "value":
+            rules.append(_limits(data, vals[0], vals[1]) + (vals[2],))
+        elif kind == "quantile":
+            sel = data[data >= vals[0]]
+            rules.append(_limits(data, float(np.quantile(sel, vals[1])), float(np.quantile(sel, vals[2]))) + (vals[3],))
+        else:
+            return None
+    return rules if len(rules) <= 4 else None
+
+
+# ---- optimiser / schedule configuration -------------------------------------------------------------------
+@dataclass
+class FusedOptimizer:
+    """What configure_optimizer returns here: the settings the fused per-network kernel consumes
+    (torch.optim defaults: betas (0.9, 0.999), eps 1e-8, no weight decay)."""
+    name: str
+    lr: float
+    betas: tuple = (0.9, 0.999)
+    eps: float = 1e-8
+    milestones: tuple = ()
+    gamma: float = 1.0
+
+    def lr_at(self, step_1based: int) -> float:
+        lr = self.lr
+        for m in self.milestones:
+            if m <= step_1based - 1:
+                lr *= self.gamma
+        return lr
+
+
+def configure_optimizer(parameters, optimizer: str, lr: float) -> FusedOptimizer:
+    if optimizer not in ("Adam", "Adamax", "SGD"):
+        raise NotImplementedError(optimizer)
+    return FusedOptimizer(optimizer, float(lr))
+
+
+def configure_lr_scheduler(optimizer: FusedOptimizer, lr_scheduler_opt) -> FusedOptimizer:
+    opt = copy.deepcopy(dict(lr_scheduler_opt))
+    name = opt.pop("name")
+    if name == "MultiStepLR":
+        optimizer.milestones = tuple(sorted(int(m) for m in opt["milestones"]))
+        optimizer.gamma = float(opt.get("gamma", 0.1))
+    elif name == "none":
+        optimizer.milestones, optimizer.gamma = (), 1.0
+    else:
+        raise NotImplementedError(f"lr scheduler '{name}' is not used by any shipped config")
+    return optimizer
+
+
+# ---- dense reconstruction -----------------------------------------------------------------------------------
+def reconstruct_flattened(data_shape: Sequence[int], sample_size: int, sample_nf: Callable, device: str = "cuda",
+                          half: bool = False, coords_mode: str = "-1,1") -> torch.Tensor:
+    """Evaluate the network on the dense grid of `data_shape` ([d,h,w,C] / [h,w,C]) -> fp32 tensor of that shape.
+    When `sample_nf` is the forward of a fused SIREN the whole grid is produced by ONE decompress launch with
+    on-chip coordinates (sample_size is then irrelevant to the result); any other callable is fed coordinate
+    chunks of `sample_size` like the reference (utils/misc.py:59-92)."""
+    if half:
+        raise NotImplementedError("half=True is not part of the fused SIREN path")
+    *cshape, channels = [int(x) for x in data_shape]
+    owner = getattr(sample_nf, "__self__", None)
+    from .Networks import SIREN
+    if isinstance(owner, SIREN) and getattr(sample_nf, "__name__", "") == "forward":
+        dims = tuple(cshape) if len(cshape) == 3 else (1, *cshape)
+        grp = owner.fused_group(dims)
+        grp.set_axes(0, coords_mode)
+        return grp.decompress("float32")[0].reshape(*cshape, channels)
+    with torch.no_grad():
+        coords = create_flattened_coords(tuple(cshape), coords_mode).to(device)
+        flat = torch.zeros((coords.shape[0], channels), device=device)
+        for s in range(0, coords.shape[0], sample_size):
+            flat[s:s + sample_size] = sample_nf(coords[s:s + sample_size])
+    return flat.reshape(*cshape, channels)
+
+
+# ---- block partition (the multi-network batch) ------------------------------------------------------------------
+def cal_divide_num(d: int, h: int, w: int, Nb: int, param_size: float) -> np.ndarray:
+    """Grid (nd,nh,nw) of proper divisors whose product is the largest <= Nb, ties -> most cubic blocks
+    (utils/adaptive_blocking.py:425-460; Nb <= 0 -> param bytes / (4*1361))."""
+    if Nb <= 0:
+        Nb = max(1, int(param_size / (4 * 1361)))
+
+    def divisors(n):
+        return [1] + [i for i in range(2, n) if n % i == 0]
+
+    best, best_key = None, None
+    for nd in divisors(d):
+        for nh in divisors(h):
+            for nw in divisors(w):
+                num = nd * nh * nw
+                if num > Nb:
+                    continue
+                ext = np.array([d / nd, h / nh, w / nw])
+                var = ((ext - ext.mean()) ** 2).mean()
+                if best is None or num > best_key[0] or (num == best_key[0] and var < best_key[1]):
+                    best, best_key = np.array([nd, nh, nw]), (num, var)
+    return best
+
+
+def divide_data(data: np.ndarray, divide_type: str):
+    """'total_nd_nh_nw' / 'every_d_h_w' -> list of chunk dicts with inclusive 'd','h','w' ranges and the
+    reference's chunk names (utils/misc.py:329-366, 3-D).  Returns (chunks, None): the preview image the
+    reference also returns is not produced."""
+    if data.ndim != 4:
+        raise NotImplementedError("3-D volumes [d,h,w,c] only")
+    kind, a, b, c = divide_type.split("_")
+    a, b, c = int(a), int(b), int(c)
+    if "total" in kind:
+        ext = (int(data.shape[0] / a), int(data.shape[1] / b), int(data.shape[2] / c))
+    elif "every" in kind:
+        ext = (a, b, c)
+    else:
+        raise NotImplementedError(divide_type)
+    cuts = [list(range(0, data.shape[k], ext[k])) + [data.shape[k]] for k in range(3)]
+    chunks = []
+    for z0, z1 in zip(cuts[0][:-1], cuts[0][1:]):
+        for y0, y1 in zip(cuts[1][:-1], cuts[1][1:]):
+            for x0, x1 in zip(cuts[2][:-1], cuts[2][1:]):
+                blk = data[z0:z1, y0:y1, x0:x1]
+                chunks.append({"data": blk, "d": [z0, z1 - 1], "h": [y0, y1 - 1], "w": [x0, x1 - 1],
+                               "total_size": data.size, "size": blk.size,
+                               "name": f"d_{z0}_{z1 - 1}-h_{y0}_{y1 - 1}-w_{x0}_{x1 - 1}"})
+    return chunks, None
+
+
+def alloc_param(data_chunk_list: List[dict], param_size: float, param_alloc: str, param_size_thres: float):
+    """Split the byte budget over blocks (equal | by_size | by_var) and drop blocks below the threshold,
+    re-allocating until stable (utils/misc.py:395-428)."""
+    chunks = list(data_chunk_list)
+    while True:
+        if param_alloc == "equal":
+            for c in chunks:
+                c["param_size"] = param_size / len(chunks)
+        elif param_alloc == "by_size":
+            for c in chunks:
+                c["param_size"] = param_size * c["size"] / c["total_size"]
+        elif param_alloc == "by_var":
+            var = [((c["data"] - c["data"].mean()) ** 2).mean() for c in chunks]
+            total = 0
+            for v in var:
+                total += v
+            for c, v in zip(chunks, var):
+                c["param_size"] = float(param_size * v / total)
+        else:
+            raise NotImplementedError(f"param_alloc '{param_alloc}' needs the FFT block feature (not on the hot path)")
+        kept = [c for c in chunks if c["param_size"] >= param_size_thres]
+        if len(kept) == len(chunks):
+            return kept
+        chunks = kept
+
+
+def merge_divided_data(decompressed_data_chunk_list: List[dict], data_shape) -> np.ndarray:
+    """Zero canvas, add each block at its inclusive range, clip to the dtype maximum, cast (utils/misc.py:430-445)."""
+    first = decompressed_data_chunk_list[0]["data"]
+    canvas = np.zeros(data_shape, dtype=np.float32)
+    for c in decompressed_data_chunk_list:
+        canvas[c["d"][0]:c["d"][1] + 1, c["h"][0]:c["h"][1] + 1, c["w"][0]:c["w"][1] + 1] += c["data"]
+    return canvas.clip(None, get_type_max(first)).astype(first.dtype)
+
+
+# ---- quality metrics ------------------------------------------------------------------------------------------
+def cal_mse(data1: np.ndarray, data2: np.ndarray):
+    return ((data1 - data2) ** 2).mean()
+
+
+def cal_psnr(origin_data: np.ndarray, decompressed_data: np.ndarray, data_range) -> float:
+    err = origin_data / data_range - decompressed_data / data_range
+    return -10 * np.log10(np.mean(np.power(err, 2)))
+
+
+def _gauss_window(size: int = 11, sigma: float = 1.5) -> torch.Tensor:
+    x = torch.arange(size, dtype=torch.float) - size // 2
+    g = torch.exp(-(x ** 2) / (2 * sigma ** 2))
+    return g / g.sum()
+
+
+def _ssim_slice(x: torch.Tensor, y: torch.Tensor, data_range: float) -> torch.Tensor:
+    """2-D SSIM of [1,C,H,W] images: separable 11-tap Gaussian, valid convolution, K=(0.01,0.03) (utils/ssim.py)."""
+    import torch.nn.functional as F
+    ch = x.shape[1]
+    win = _gauss_window().to(x.device, x.dtype)
+
+    def blur(t):
+        for axis, n in ((2, t.shape[2]), (3, t.shape[3])):
+            if n >= win.numel():
+                shape = [ch, 1, 1, 1]
+                shape[axis] = -1
+                t = F.conv2d(t, win.view(1, 1, -1, 1).expand(ch, 1, -1, 1) if axis == 2
+                             else win.view(1, 1, 1, -1).expand(ch, 1, 1, -1), groups=ch)
+        return t
+
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    mx, my = blur(x), blur(y)
+    sxx, syy, sxy = blur(x * x) - mx * mx, blur(y * y) - my * my, blur(x * y) - mx * my
+    cs = (2 * sxy + c2) / (sxx + syy + c2)
+    return (((2 * mx * my + c1) / (mx * mx + my * my + c1)) * cs).flatten(2).mean(-1).mean()
+
+
+def cal_ssim(origin_data: np.ndarray, decompressed_data: np.ndarray, data_range, device: str = "cpu") -> float:
+    """Mean over depth slices of the 2-D SSIM (utils/misc.py:458-475)."""
+    a = torch.from_numpy(np.ascontiguousarray(origin_data)).to(device)
+    b = torch.from_numpy(np.ascontiguousarray(decompressed_data)).to(device)
+    if a.dim() == 3:
+        return float(_ssim_slice(a.permute(2, 0, 1)[None], b.permute(2, 0, 1)[None], data_range))
+    total = 0.0
+    for i in range(a.shape[0]):
+        total += _ssim_slice(a[i].permute(2, 0, 1)[None], b[i].permute(2, 0, 1)[None], data_range)
+    return float(total / a.shape[0])
+
+
+def eval_performance(steps: int, data1: np.ndarray, data2: np.ndarray, Log=None, mse=True, psnr=True, ssim=True,
+                     device: str = "cpu") -> dict:
+    out = {"steps": steps}
+    rng = get_type_max(data1)
+    a, b = data1.astype(np.float32), data2.astype(np.float32)
+    if mse:
+        out["mse"] = cal_mse(a, b)
+    if psnr:
+        out["psnr"] = cal_psnr(a, b, rng)
+    if ssim:
+        out["ssim"] = cal_ssim(a, b, rng, device)
+    if Log is not None:
+        Log.log_metrics({k: v for k, v in out.items() if k != "steps"}, steps)
+    return out

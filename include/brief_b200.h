@@ -1,0 +1,191 @@
+/*
+ * brief_b200.h — C ABI of the B200-native BRIEF hot path (libbrief_b200.so).
+ *
+ * The reference (RichealYoung/BRIEF_PyTorch) has no FFI: its boundary for this path is Python
+ * (SURVEY.md section 8b).  This header is the C-ABI that sits BENEATH a Python mirror of that
+ * boundary (package brief_pytorch_b200).  Every entry point names the reference interface whose
+ * work it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *  - All functions return 0 (BRIEF_OK) on success and a negative BriefStatus otherwise;
+ *    brief_last_error() returns a thread-local message for the last failure.
+ *  - "dev_" pointers are device pointers owned by the caller (e.g. torch allocations),
+ *    "host_" pointers are ordinary host memory.  `stream` is a cudaStream_t passed as void*.
+ *    All work is enqueued on that stream; calls taking host pointers synchronise it.
+ *  - A BriefGroup is a set of independent per-block SIREN networks (one per volume block,
+ *    main.py:484-532) that are evaluated / fitted together in grouped kernel launches.
+ *  - Parameters cross the ABI in the reference's `parameters()` order, fp32, exactly as
+ *    utils/ModelSave.py:32-51 writes them: W_0[f][in], b_0[f], W_1[f][f], b_1[f], ...,
+ *    W_{L-1}[out][f], b_{L-1}[out]  (row-major [out][in]).
+ *  - There is no CPU fallback: without a CUDA device every compute entry point fails with
+ *    BRIEF_ERR_CUDA.
+ */
+#ifndef BRIEF_B200_H_
+#define BRIEF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRIEF_B200_ABI_VERSION 1
+
+typedef enum BriefStatus {
+  BRIEF_OK = 0,
+  BRIEF_ERR_INVALID = -1,     /* bad argument / unsupported configuration            */
+  BRIEF_ERR_CUDA = -2,        /* CUDA runtime error (message has the CUDA string)    */
+  BRIEF_ERR_UNSUPPORTED = -3, /* valid request outside what this build implements    */
+  BRIEF_ERR_STATE = -4        /* call order violated (e.g. fit before bind_volume)   */
+} BriefStatus;
+
+/* Arithmetic of the hidden-layer contractions. First/last layer, loss, optimiser: always fp32. */
+typedef enum BriefPrecision {
+  BRIEF_PREC_FP32 = 0, /* CUDA-core fp32 everywhere (exact mode; any width up to the smem limit) */
+  BRIEF_PREC_BF16 = 1, /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM          */
+  BRIEF_PREC_AUTO = 2  /* BF16 where the fused tensor-core kernel supports the shape, else FP32  */
+} BriefPrecision;
+
+typedef enum BriefDType { BRIEF_U8 = 0, BRIEF_U16 = 1, BRIEF_F32 = 2 } BriefDType;
+
+typedef enum BriefSamplerMode {
+  BRIEF_SAMPLE_FULL_BLOCK = 0,   /* RandomCubeSampler with pop_size==1: every step = whole block in
+                                    voxel order (main.py:38-125 with the shipped cube_len)         */
+  BRIEF_SAMPLE_RANDOM_POINTS = 1 /* RandompointSampler (main.py:126-163): `batch` indices with
+                                    replacement per step                                           */
+} BriefSamplerMode;
+
+typedef enum BriefOptimizer { BRIEF_OPT_ADAMAX = 0, BRIEF_OPT_ADAM = 1, BRIEF_OPT_SGD = 2 } BriefOptimizer;
+
+/* One network = SIREN(coords_channel, data_channel, features, layers, w0) of utils/Networks.py:246-266
+ * bound to one block of `dims` voxels.  Hidden-layer omega is the reference's hard-wired 30
+ * (utils/Networks.py:227-229,259) unless overridden here. */
+typedef struct BriefNetDesc {
+  int32_t coords_channel; /* 2 or 3 */
+  int32_t data_channel;   /* 1 (the fused kernels support a single output channel)        */
+  int32_t features;       /* f                                                               */
+  int32_t layers;         /* L >= 2: 1 input sine layer, L-2 hidden sine layers, 1 linear    */
+  float w0;               /* first-layer omega                                               */
+  float w_hidden;         /* hidden-layer omega, 30 in the reference                         */
+  int32_t dims[3];        /* block extent (d,h,w); for 2-D data d = 1 and coords are (h,w)   */
+} BriefNetDesc;
+
+/* parse_weight 'value_l_h_s' rules (utils/misc.py:293-297), applied in order on the raw voxel. */
+typedef struct BriefWeightRule {
+  float lo, hi, scale;
+} BriefWeightRule;
+#define BRIEF_MAX_WEIGHT_RULES 4
+
+typedef struct BriefOptConfig {
+  int32_t kind;    /* BriefOptimizer; configure_optimizer utils/misc.py:174-183                */
+  float lr;        /* initial lr (lr_phi)                                                      */
+  float beta1, beta2, eps; /* torch defaults 0.9, 0.999, 1e-8                                  */
+  int32_t n_milestones;    /* MultiStepLR (utils/misc.py:187-188); 0 = constant lr             */
+  int64_t milestones[8];
+  float gamma;
+} BriefOptConfig;
+
+typedef struct BriefGroup BriefGroup;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int brief_abi_version(void);
+const char* brief_last_error(void);
+int brief_device_count(int* out_count);
+
+/* torch.linspace(lo, hi, n) on the CPU, bit-for-bit (utils/dataset.py:22-32,47-58 call sites).
+ * Used to build the per-axis coordinate tables when the caller does not supply them. */
+int brief_linspace(float lo, float hi, int32_t n, float* host_out);
+
+/* ---- group life cycle ------------------------------------------------------------------------ */
+/* Replaces: init_phi / SIREN.__init__ (utils/Networks.py:246-266, 800-802) for n_nets networks and
+ * the per-block process farm of main.py:547-579.  Parameters start at zero: load them with
+ * brief_group_set_params (initialisation stays in Python so that it is bit-identical to torch's
+ * CPU generator under the same seed). */
+int brief_group_create(const BriefNetDesc* nets, int32_t n_nets, int32_t device, int32_t precision,
+                       BriefGroup** out);
+void brief_group_destroy(BriefGroup* g);
+int brief_group_num_nets(const BriefGroup* g);
+int brief_group_param_count(const BriefGroup* g, int32_t net);      /* SIREN.calc_param_count :291-297 */
+int brief_group_precision(const BriefGroup* g, int32_t net);        /* resolved BriefPrecision          */
+
+/* Replaces load_model / save_model's tensor traffic (utils/ModelSave.py:8-51). Packed fp32, host. */
+int brief_group_set_params(BriefGroup* g, int32_t net, const float* host_packed, void* stream);
+int brief_group_get_params(BriefGroup* g, int32_t net, float* host_packed, void* stream);
+/* Gradients of the last brief_fit_step (same packed order); for parity tests. */
+int brief_group_get_grads(BriefGroup* g, int32_t net, float* host_packed, void* stream);
+/* Test hook: overwrite the gradient arena of one network (packed order), so that brief_opt_step can
+ * be checked against torch.optim on identical gradients. */
+int brief_group_set_grads(BriefGroup* g, int32_t net, const float* host_packed, void* stream);
+/* Optimiser state (exp_avg, exp_inf / exp_avg_sq) of torch.optim, packed order; tests + resume. */
+int brief_group_get_opt_state(BriefGroup* g, int32_t net, float* host_m, float* host_v, void* stream);
+int brief_group_reset_opt_state(BriefGroup* g, void* stream);
+
+/* Per-axis coordinate tables (create_coords, utils/dataset.py:11-35): axis k of network `net`
+ * has dims[k] fp32 entries.  If never called the tables are brief_linspace(-1, 1, dims[k]). */
+int brief_group_set_axes(BriefGroup* g, int32_t net, const float* host_d, const float* host_h,
+                         const float* host_w, void* stream);
+
+/* ---- data binding ----------------------------------------------------------------------------- */
+/* Replaces normalize_data (utils/io.py:67-80), parse_weight (utils/misc.py:272-307) and the
+ * samplers' materialised fp32 copies (main.py:134-139): the raw block stays in HBM in its own
+ * dtype and is normalised on chip as ((x - vmin) / (vmax - vmin)) * (hi - lo) + lo, fp32, the
+ * reference's operation order.  `dev_weight` (fp32, one per voxel) may be NULL, in which case
+ * `rules` are evaluated on the raw voxel (weight 1 when no rule matches).  `tau` is the normalised
+ * weight threshold of main.py:380-383 (0 disables the override, like the reference's truthiness test). */
+int brief_group_bind_volume(BriefGroup* g, int32_t net, const void* dev_raw, int32_t dtype, float vmin,
+                            float vmax, float lo, float hi, const float* dev_weight,
+                            const BriefWeightRule* rules, int32_t n_rules, float tau);
+/* Sampler of main.py:367-371 for this network. `batch` is ignored for FULL_BLOCK (= voxel count). */
+int brief_group_set_sampler(BriefGroup* g, int32_t net, int32_t mode, int32_t batch);
+
+/* ---- hot path ----------------------------------------------------------------------------------- */
+/* One training step for EVERY network of the group: sampler gather + forward + weighted L2
+ * (datal2, main.py:176-182) + backward (main.py:385-396).  Gradients stay on the device.
+ * dev_idx: NULL = on-device sampler (Philox4x32-10 keyed by seed, step), or the replayed indices of
+ * the reference's torch.randint stream, int64, all networks concatenated in order (RANDOM_POINTS
+ * networks contribute `batch` entries each, FULL_BLOCK networks none).
+ * dev_loss: n_nets floats (mean weighted loss per network), may be NULL. */
+int brief_fit_step(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, float* dev_loss,
+                   void* stream);
+/* optimizer.step() + lr_scheduler.step() (main.py:399-400, utils/misc.py:174-197) for every network,
+ * consuming the gradients of the preceding brief_fit_step.  `lr` is this step's learning rate and
+ * `t` the 1-based optimiser step count (bias correction). */
+int brief_opt_step(BriefGroup* g, int32_t kind, float lr, float beta1, float beta2, float eps, int64_t t,
+                   void* stream);
+/* The loop of main.py:385-400 for `n_steps` steps starting after `steps_done` completed steps, entirely
+ * enqueued from C (no per-step host sync, no loss.item()).  dev_loss_hist: NULL or n_steps*n_nets floats. */
+int brief_fit_run(BriefGroup* g, const BriefOptConfig* cfg, uint64_t seed, int64_t steps_done, int64_t n_steps,
+                  float* dev_loss_hist, void* stream);
+
+/* SIREN.forward on caller coordinates (utils/Networks.py:269-271): dev_coords [n][coords_channel] fp32
+ * -> dev_out [n][1] fp32.  dev_layers (optional, may be NULL): pre-activations z_l of every layer,
+ * layout [layers-1][n][features] fp32, for per-layer parity checks. */
+int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n, float* dev_out,
+                  float* dev_layers, void* stream);
+
+/* Replaces reconstruct_flattened + invnormalize_data (utils/misc.py:59-92, utils/io.py:136-147) for every
+ * network of the group in one launch: dense grid generated on chip from the axis tables, evaluated, then
+ * ((y - lo) / (hi - lo)) clipped to [0,1], * (vmax - vmin) + vmin, truncating cast to out_dtype.
+ * host_dev_out[i] is the device destination of network i (dims[0]*dims[1]*dims[2] elements, contiguous);
+ * out_dtype BRIEF_F32 skips the inverse normalisation and stores the raw network output.
+ * vmin/vmax/lo/hi default to the values given to brief_group_bind_volume, or override with
+ * brief_group_set_denorm for decode-only groups. */
+int brief_group_set_denorm(BriefGroup* g, int32_t net, float vmin, float vmax, float lo, float hi);
+int brief_decompress(BriefGroup* g, void* const* host_dev_out, int32_t out_dtype, void* stream);
+
+/* The reference samplers' three outputs materialised (main.py:156-160), for parity and for the
+ * HBM-bandwidth measurement of the gather: coords [batch][coords_channel], data [batch], weight [batch]. */
+int brief_gather(BriefGroup* g, int32_t net, const int64_t* dev_idx, int64_t batch, float* dev_coords,
+                 float* dev_data, float* dev_weight, void* stream);
+/* The on-device sampler's index stream for (seed, step, net): int64 [batch] in [0, pop). */
+int brief_sample_indices(uint64_t seed, uint64_t step, int32_t net, int64_t batch, int64_t pop,
+                         int64_t* dev_out, void* stream);
+
+/* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
+int64_t brief_launch_count(void);
+void brief_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRIEF_B200_H_ */
