@@ -371,7 +371,9 @@ void linspace_host(float lo, float hi, int n, float* out) {
   if (n == 1) { out[0] = lo; return; }
   const float step = (hi - lo) / (float)(n - 1);
   const int half = n / 2;
-  for (int i = 0; i < n; ++i) out[i] = i < half ? lo + step * (float)i : hi - step * (float)(n - i - 1);
+  // torch's vectorised CPU kernel contracts the multiply-add (AVX2/AVX-512 fmadd), so fmaf reproduces it
+  for (int i = 0; i < n; ++i)
+    out[i] = i < half ? std::fmaf(step, (float)i, lo) : std::fmaf(-step, (float)(n - i - 1), hi);
 }
 
 }  // namespace
@@ -631,6 +633,16 @@ int brief_fit_step(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_
   RC(ensure_wpack(g, st));
   RC(launch_fit_kernels(g, dev_idx, seed, step, st));
   return launch_opt_kernel(g, true, false, 0, 0, 0, 0, 0, 0, dev_loss ? dev_loss : g->d_loss_scratch.p, st);
+}
+
+int brief_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, void* stream) {
+  if (!g) return fail(BRIEF_ERR_INVALID, "null group");
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(check_bound(g));
+  RC(finalize(g, st));
+  RC(ensure_wpack(g, st));
+  return launch_fit_kernels(g, dev_idx, seed, step, st);
 }
 
 int brief_opt_step(BriefGroup* g, int32_t kind, float lr, float beta1, float beta2, float eps, int64_t t, void* stream) {

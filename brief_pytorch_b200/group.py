@@ -202,6 +202,11 @@ class SirenGroup:
             check(self._lib.brief_fit_step(self._h, _ptr(idx), seed, step, _ptr(loss), _stream(self.device)))
         return loss
 
+    def fit_kernel_only(self, idx: Optional[torch.Tensor] = None, seed: int = 0, step: int = 0) -> None:
+        """Bench hook: launch only the fit kernel(s) (no partial reduction, no optimiser)."""
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_fit_kernels(self._h, _ptr(idx), seed, step, _stream(self.device)))
+
     def opt_step(self, kind: str = "Adamax", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  t: Optional[int] = None) -> None:
         if t is None:

@@ -147,6 +147,9 @@ int brief_group_set_sampler(BriefGroup* g, int32_t net, int32_t mode, int32_t ba
  * dev_loss: n_nets floats (mean weighted loss per network), may be NULL. */
 int brief_fit_step(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, float* dev_loss,
                    void* stream);
+/* Bench / profiling hook: ONLY the fit kernel(s) of brief_fit_step (per-slice gradient partials are produced but not
+ * reduced), so that bench.py can time the dominant kernel alone with CUDA events on `stream`. */
+int brief_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, void* stream);
 /* optimizer.step() + lr_scheduler.step() (main.py:399-400, utils/misc.py:174-197) for every network,
  * consuming the gradients of the preceding brief_fit_step.  `lr` is this step's learning rate and
  * `t` the 1-based optimiser step count (bias correction). */
