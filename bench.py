@@ -3,7 +3,7 @@
 beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload vessel|vessel64|config1]
-                    [--precision auto|bf16|fp32]
+                    [--precision auto|f16|fp32]
 
 Workload at N=1 = BASELINE.json configs[1]: DivideTask opt/DivideTask/vessel.yaml on a synthetic 64x512x512 uint16
 volume (ratio 128, `adaptotal_-1_-1_-1_4` -> 4 blocks of 64x256x256, one SIREN L=7 f=56 w0=10 per block,
@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vessel", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
@@ -368,7 +368,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": prec if prec == "bf16" else "f32", "data": "synthetic",
+            "dtype": prec if prec == "f16" else "f32", "data": "synthetic",
             "config": {"workload": plan["desc"], "blocks_per_gpu": n_local, "block_shape": list(bs),
                        "features": plan["features"], "layers": plan["layers"], "batch_per_block": plan["batch"],
                        "precision": prec, "l2": "flushed (256 MiB write) between timed steps",

@@ -11,7 +11,7 @@ from . import build as _build
 
 c_i32, c_i64, c_u64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
 
-PREC_FP32, PREC_BF16, PREC_AUTO = 0, 1, 2
+PREC_FP32, PREC_F16, PREC_AUTO = 0, 1, 2
 DT_U8, DT_U16, DT_F32 = 0, 1, 2
 SAMPLE_FULL_BLOCK, SAMPLE_RANDOM_POINTS = 0, 1
 OPT_ADAMAX, OPT_ADAM, OPT_SGD = 0, 1, 2

@@ -52,7 +52,7 @@ int fail(int code, const char* fmt, ...) {
 constexpr size_t kSmemLimit = 200 * 1024;       // dynamic smem budget of the fp32 kernels
 constexpr size_t kPartialCapBytes = 16u << 20;  // gradient-partial budget per network
 constexpr int kTcTile = 128;                    // samples per tcgen05 tile (UMMA M)
-constexpr int kTcMinTilesPerSlice = 8;
+constexpr int kTcCtasPerSm = 1;                 // the fit kernel keeps one CTA per SM (shared memory bound)
 constexpr int kTcEvalTilesPerBlock = 64;
 constexpr int kBuckets = 9;  // F_PAD / 16 in 1..8
 
@@ -86,6 +86,7 @@ struct WorkTable {  // block -> (network, local work index) for one kernel famil
 
 struct BriefGroup {
   int device = 0;
+  int num_sms = 148;
   int n_nets = 0;
   std::vector<NetDev> nets;
   long long total_P = 0, total_axis = 0;
@@ -97,7 +98,7 @@ struct BriefGroup {
   DevBuf<void*> d_outptrs;
   bool nets_dirty = true;   // host NetDev array differs from the device copy
   bool work_dirty = true;   // sampler changed: rebuild the fit decomposition
-  bool wpack_dirty = true;  // params changed since the bf16 operand image was packed
+  bool wpack_dirty = true;  // params changed since the fp16 operand image was packed
   bool any_tc = false, any_simt = false;
   // fit
   int simt_fit_tm = 0;
@@ -107,6 +108,7 @@ struct BriefGroup {
   int simt_eval_tm = 0;
   size_t simt_eval_smem = 0;
   WorkTable simt_eval, tc_eval[kBuckets];
+  int tc_L[kBuckets] = {0};  // deepest network per tensor-core bucket (sizes the dynamic shared memory)
 };
 
 namespace {
@@ -189,7 +191,7 @@ struct TableBuilder {
 int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   int tm = 128;
   for (auto& n : g->nets) {
-    if (n.prec == BRIEF_PREC_BF16) continue;
+    if (n.prec == BRIEF_PREC_F16) continue;
     const int t = simt_pick_tm(n.F4, n.L, false, kSmemLimit);
     if (t == 0)
       return fail(BRIEF_ERR_UNSUPPORTED, "features=%d exceed the fp32 kernel's shared-memory budget", n.f);
@@ -201,13 +203,14 @@ int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
   for (int i = 0; i < g->n_nets; ++i) {
     const NetDev& n = g->nets[i];
-    if (n.prec == BRIEF_PREC_BF16) {
+    if (n.prec == BRIEF_PREC_F16) {
       const int b = n.F_PAD / 16;
       const long long tiles = (n.n_vox + kTcTile - 1) / kTcTile;
       const long long blocks = (tiles + kTcEvalTilesPerBlock - 1) / kTcEvalTilesPerBlock;
       if (tp[b].back() + blocks > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "group too large for one launch");
       tn[b].push_back(i);
       tp[b].push_back((int)(tp[b].back() + blocks));
+      g->tc_L[b] = std::max(g->tc_L[b], n.L);
     } else {
       const long long tiles = (n.n_vox + tm - 1) / tm;
       if (sp.back() + tiles > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "group too large for one launch");
@@ -228,7 +231,7 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   int tm = 128;
   g->any_simt = g->any_tc = false;
   for (auto& n : g->nets) {
-    if (n.prec == BRIEF_PREC_BF16) { g->any_tc = true; continue; }
+    if (n.prec == BRIEF_PREC_F16) { g->any_tc = true; continue; }
     g->any_simt = true;
     const int t = simt_pick_tm(n.F4, n.L, true, kSmemLimit);
     if (t == 0)
@@ -237,6 +240,15 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   }
   g->simt_fit_tm = tm;
   g->simt_fit_smem = 0;
+  // tensor-core networks: one CTA per slice, slices sized so that all networks together fill one wave of CTAs
+  long long tc_tiles = 0;
+  for (auto& n : g->nets)
+    if (n.prec == BRIEF_PREC_F16) {
+      const long long b = n.mode == BRIEF_SAMPLE_FULL_BLOCK ? n.n_vox : (long long)n.batch;
+      tc_tiles += (b + kTcTile - 1) / kTcTile;
+    }
+  const long long tc_wave = (long long)g->num_sms * kTcCtasPerSm;
+  const long long tc_tps = std::max<long long>(1, (tc_tiles + tc_wave - 1) / tc_wave);
   long long slice_total = 0, part_total = 0, idx_total = 0;
   std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets], op{0}, on;
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
@@ -250,12 +262,12 @@ int finalize(BriefGroup* g, cudaStream_t st) {
       n.idx_off = idx_total;
       idx_total += n.batch;
     }
-    const bool tc = n.prec == BRIEF_PREC_BF16;
+    const bool tc = n.prec == BRIEF_PREC_F16;
     const int tile = tc ? kTcTile : tm;
     const long long n_tiles = ((long long)n.batch + tile - 1) / tile;
     const long long max_slices = std::max<long long>(1, (long long)(kPartialCapBytes / ((size_t)n.P_dev * 4)));
     long long tps = (n_tiles + max_slices - 1) / max_slices;
-    if (tc) tps = std::max<long long>(tps, kTcMinTilesPerSlice);
+    if (tc) tps = std::max<long long>(tps, tc_tps);
     tps = std::max<long long>(tps, 1);
     n.slice_len = (int)(tps * tile);
     n.n_slices = (int)((n_tiles + tps - 1) / tps);
@@ -321,7 +333,7 @@ int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uin
     a.work_net = g->d_fit_tables.p + g->tc_fit[b].off_net;
     a.n_work = g->tc_fit[b].n;
     a.TM = kTcTile;
-    LAUNCH(launch_tc_fit(a, 16 * b, g->tc_fit[b].blocks, st));
+    LAUNCH(launch_tc_fit(a, 16 * b, g->tc_L[b], g->tc_fit[b].blocks, st));
   }
   return 0;
 }
@@ -413,6 +425,8 @@ int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device
   CU(cudaSetDevice(device));
   BriefGroup* g = new BriefGroup();
   g->device = device;
+  cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (g->num_sms < 1) g->num_sms = 148;
   g->n_nets = n_nets;
   g->nets.resize(n_nets);
   auto bail = [&](int rc) { brief_group_destroy(g); return rc; };
@@ -446,12 +460,12 @@ int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device
     g->total_axis += n.d + n.h + n.w;
     if (g->total_axis > 0x7fffffffLL) return bail(fail(BRIEF_ERR_UNSUPPORTED, "axis table arena too large"));
     const bool tc_ok = tc_supported(n.f, n.L, n.in_dim, n.out_dim);
-    if (precision == BRIEF_PREC_BF16 && !tc_ok)
+    if (precision == BRIEF_PREC_F16 && !tc_ok)
       return bail(fail(BRIEF_ERR_UNSUPPORTED,
                        "net %d: features=%d layers=%d is outside the fused tcgen05 kernel's TMEM/SMEM budget; "
                        "use BRIEF_PREC_FP32 or BRIEF_PREC_AUTO", i, n.f, n.L));
-    n.prec = (precision == BRIEF_PREC_FP32 || !tc_ok) ? BRIEF_PREC_FP32 : BRIEF_PREC_BF16;
-    if (n.prec == BRIEF_PREC_BF16) {
+    n.prec = (precision == BRIEF_PREC_FP32 || !tc_ok) ? BRIEF_PREC_FP32 : BRIEF_PREC_F16;
+    if (n.prec == BRIEF_PREC_F16) {
       n.F_PAD = tc_fpad(n.f);
       n.wpack_off = (long long)g->total_wpack;
       g->total_wpack += (tc_wpack_bytes(n.F_PAD, n.L) + 127) & ~(size_t)127;
@@ -699,12 +713,12 @@ int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n
   a.out_f32 = dev_out;
   a.layers_out = dev_layers;
   a.wpack = g->d_wpack.p;
-  if (nd.prec == BRIEF_PREC_BF16) {
+  if (nd.prec == BRIEF_PREC_F16) {
     RC(ensure_wpack(g, st));
     const long long tiles = (n + kTcTile - 1) / kTcTile;
     const long long blocks = (tiles + kTcEvalTilesPerBlock - 1) / kTcEvalTilesPerBlock;
     a.TM = kTcTile;
-    LAUNCH(launch_tc_eval(a, nd.F_PAD, (int)blocks, st));
+    LAUNCH(launch_tc_eval(a, nd.F_PAD, nd.L, (int)blocks, st));
   } else {
     const int tm = simt_pick_tm(nd.F4, nd.L, false, kSmemLimit);
     if (tm == 0) return fail(BRIEF_ERR_UNSUPPORTED, "features=%d exceed the fp32 kernel's shared-memory budget", nd.f);
@@ -749,7 +763,7 @@ int brief_decompress(BriefGroup* g, void* const* host_dev_out, int32_t out_dtype
     a.work_net = g->d_eval_tables.p + g->tc_eval[b].off_net;
     a.n_work = g->tc_eval[b].n;
     a.TM = kTcTile;
-    LAUNCH(launch_tc_eval(a, 16 * b, g->tc_eval[b].blocks, st));
+    LAUNCH(launch_tc_eval(a, 16 * b, g->tc_L[b], g->tc_eval[b].blocks, st));
   }
   return 0;
 }

@@ -56,8 +56,8 @@ struct NetDev {
   long long part_off;          // floats, into the gradient-partials arena (n_slices slots of P_dev)
   // tensor-core path
   int prec;                    // resolved BriefPrecision
-  int F_PAD;                   // padded width of the bf16 operand image (multiple of 16, > f)
-  long long wpack_off;         // bytes, into the bf16 packed-weight arena
+  int F_PAD;                   // padded width of the fp16 operand image (multiple of 16, > f)
+  long long wpack_off;         // bytes, into the fp16 packed-weight arena
 };
 
 // ---- padded device layout offsets (floats, relative to param_off) --------------------------

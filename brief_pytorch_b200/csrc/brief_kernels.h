@@ -67,7 +67,7 @@ struct OptArgs {
   float eps;
   float bc2_sqrt;    // sqrt(1 - beta2^t) (Adam)
   int apply;         // 0 = only reduce partials into grads / loss (brief_fit_step)
-  unsigned char* wpack;  // refreshed bf16 operand image (tensor-core networks) or NULL
+  unsigned char* wpack;  // refreshed fp16 operand image (tensor-core networks) or NULL
 };
 
 // brief_simt.cu
@@ -91,7 +91,7 @@ int tc_fpad(int f);
 size_t tc_wpack_bytes(int F_PAD, int L);
 size_t tc_eval_smem(int F_PAD, int L);
 size_t tc_fit_smem(int F_PAD, int L);
-cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int n_blocks, cudaStream_t st);
-cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int n_blocks, cudaStream_t st);
+cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st);
+cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st);
 
 }  // namespace brief

@@ -1,5 +1,5 @@
 // brief_opt.cu — per-network fused optimiser step for the whole group in ONE launch, plus the
-// refresh of the bf16 operand image used by the tcgen05 kernels.
+// refresh of the fp16 operand image used by the tcgen05 kernels.
 //
 // Reference work replaced: torch.optim.Adamax / Adam / SGD .step() (configure_optimizer,
 // utils/misc.py:174-183; main.py:399) — ~6 tiny ATen ops x 2L tensors per network per step — and
@@ -16,7 +16,7 @@
 // plus 4 B/param/slice of partial traffic; HBM/L2-bound and tiny next to the fit kernel.
 #include "brief_common.cuh"
 #include "brief_kernels.h"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace brief {
 
@@ -86,11 +86,14 @@ cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// ---- bf16 operand image for the tcgen05 kernels ----------------------------------------------------
+// ---- fp16 operand image for the tcgen05 kernels ----------------------------------------------------
 // Image of network n (bytes, at wpack + n.wpack_off), F = F_PAD, NH = L-2:
-//   [NH] hidden weights, bf16, UMMA no-swizzle core-matrix layout: element (o,k) of layer l at
+//   [NH] hidden weights, fp16, UMMA no-swizzle core-matrix layout: element (o,k) of layer l at
 //        l*F*F*2 + ((k/8)*(F/8) + o/8)*128 + (o%8)*16 + (k%8)*2       (8x8 cores, K contiguous)
 //   then fp32: first layer float4 (wx,wy,wz,b0) x F | omega*bias [NH][F] | Wlast [F] | blast,0,0,0
+// Pad column f (the first unused feature) is the constant-one feature of the fit kernel: its weights are zero
+// and its "bias" makes the sine argument pi/2, so every activation buffer carries a 1.0 in column f and the
+// bias gradients fall out of the dW contractions.
 __global__ void pack_kernel(const NetDev* nets, int n_nets, const float* __restrict__ params, unsigned char* wpack) {
   for (int net_id = blockIdx.y; net_id < n_nets; net_id += gridDim.y) {
   const NetDev& n = nets[net_id];
@@ -106,17 +109,18 @@ __global__ void pack_kernel(const NetDev* nets, int n_nets, const float* __restr
       const int o = r / F, k = r - o * F;
       const float w = (o < f && k < f) ? P[dl_W(n, l + 1) + o * F4 + k] : 0.f;
       const size_t off = (size_t)l * F * F * 2 + ((size_t)(k >> 3) * (F >> 3) + (o >> 3)) * 128 + (o & 7) * 16 + (k & 7) * 2;
-      *reinterpret_cast<__nv_bfloat16*>(img + off) = __float2bfloat16_rn(w);
+      *reinterpret_cast<__half*>(img + off) = __float2half_rn(w);
     } else {
       const int j = i - n_hidden;
       float* side = reinterpret_cast<float*>(img + (size_t)n_hidden * 2);
       float val;
       if (j < 4 * F) {
         const int o = j >> 2, c = j & 3;
-        val = (o < f) ? (c < 3 ? P[dl_W0(n) + 4 * o + c] : P[dl_b0(n) + o]) : 0.f;
+        val = (o < f) ? (c < 3 ? P[dl_W0(n) + 4 * o + c] : P[dl_b0(n) + o])
+                      : (o == f && c == 3 ? __fdiv_rn(1.57079632679f, n.w0) : 0.f);
       } else if (j < 4 * F + NH * F) {
         const int q = j - 4 * F, l = q / F, o = q - l * F;
-        val = (o < f) ? __fmul_rn(n.wh, P[dl_b(n, l + 1) + o]) : 0.f;
+        val = (o < f) ? __fmul_rn(n.wh, P[dl_b(n, l + 1) + o]) : (o == f ? 1.57079632679f : 0.f);
       } else if (j < 4 * F + NH * F + F) {
         const int k = j - 4 * F - NH * F;
         val = (k < f) ? P[dl_Wlast(n) + k] : 0.f;

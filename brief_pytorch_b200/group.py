@@ -14,10 +14,10 @@ import numpy as np
 import torch
 
 from . import _cabi
-from ._cabi import (DT_F32, DT_U16, DT_U8, OPT_ADAM, OPT_ADAMAX, OPT_SGD, PREC_AUTO, PREC_BF16, PREC_FP32,
+from ._cabi import (DT_F32, DT_U16, DT_U8, OPT_ADAM, OPT_ADAMAX, OPT_SGD, PREC_AUTO, PREC_F16, PREC_FP32,
                     SAMPLE_FULL_BLOCK, SAMPLE_RANDOM_POINTS, check)
 
-_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16, "auto": PREC_AUTO}
+_PREC = {"fp32": PREC_FP32, "f16": PREC_F16, "bf16": PREC_F16, "auto": PREC_AUTO}  # "bf16": alias of the tensor-core mode
 _OPT = {"Adamax": OPT_ADAMAX, "Adam": OPT_ADAM, "SGD": OPT_SGD}
 _NP2DT = {"uint8": DT_U8, "uint16": DT_U16, "float32": DT_F32}
 _DT2TORCH = {DT_U8: torch.uint8, DT_U16: torch.int16, DT_F32: torch.float32}  # u16 held as int16 bit patterns
@@ -106,7 +106,7 @@ class SirenGroup:
         return len(self.specs)
 
     def precision(self, net: int) -> str:
-        return {PREC_FP32: "fp32", PREC_BF16: "bf16"}[check(self._lib.brief_group_precision(self._h, net))]
+        return {PREC_FP32: "fp32", PREC_F16: "f16"}[check(self._lib.brief_group_precision(self._h, net))]
 
     def param_count(self, net: int) -> int:
         return check(self._lib.brief_group_param_count(self._h, net))

@@ -42,8 +42,10 @@ typedef enum BriefStatus {
 /* Arithmetic of the hidden-layer contractions. First/last layer, loss, optimiser: always fp32. */
 typedef enum BriefPrecision {
   BRIEF_PREC_FP32 = 0, /* CUDA-core fp32 everywhere (exact mode; any width up to the smem limit) */
-  BRIEF_PREC_BF16 = 1, /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulate in TMEM          */
-  BRIEF_PREC_AUTO = 2  /* BF16 where the fused tensor-core kernel supports the shape, else FP32  */
+  BRIEF_PREC_F16 = 1,  /* tcgen05.mma kind::f16: fp16 operands (activations live in [-1,1], weights << 1, so
+                          fp16 carries 3 more mantissa bits than bf16 at the same tensor rate; gradients
+                          are carried with a static power-of-two scale), fp32 accumulate in TMEM     */
+  BRIEF_PREC_AUTO = 2  /* F16 where the fused tensor-core kernel supports the shape, else FP32   */
 } BriefPrecision;
 
 typedef enum BriefDType { BRIEF_U8 = 0, BRIEF_U16 = 1, BRIEF_F32 = 2 } BriefDType;

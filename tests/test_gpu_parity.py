@@ -1,5 +1,5 @@
 """Parity of the CUDA path (through the C-ABI, libbrief_b200.so) against the CPU oracle and the golden fixtures
-made from the unmodified reference.  Tolerances (BASELINE.json north_star): fp32 mode 1e-4 relative, bf16
+made from the unmodified reference.  Tolerances (BASELINE.json north_star): fp32 mode 1e-4 relative, f16
 tensor-core mode 1e-2 relative, of the tensor's max magnitude; index / byte / integer work is bit-exact."""
 import numpy as np
 import pytest
@@ -10,7 +10,7 @@ from conftest import load_gold, packed_params, unpack
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "bf16": 1e-2}
+TOL = {"fp32": 1e-4, "f16": 1e-2}
 NETS = {"c1": dict(coords_channel=3, layers=5, w0=20, features=22),
         "c2": dict(coords_channel=3, layers=7, w0=10, features=56),
         "c2small": dict(coords_channel=3, layers=7, w0=10, features=13),
@@ -28,7 +28,7 @@ def make_group(specs, prec):
     try:
         return SirenGroup(specs, 0, prec)
     except BriefError as e:
-        if e.code == -3 and prec == "bf16":
+        if e.code == -3 and prec == "f16":
             pytest.skip("shape outside the tcgen05 kernel: " + str(e))
         raise
 
@@ -42,7 +42,7 @@ def u16(t):
     return t.cpu().numpy().view(np.uint16)
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 @pytest.mark.parametrize("tag", sorted(NETS))
 def test_forward_per_layer(tag, prec):
     g, kw = load_gold("siren_" + tag), NETS[tag]
@@ -91,7 +91,7 @@ def test_device_sampler_matches_oracle_stream():
         np.testing.assert_array_equal(got, O.device_sample_indices(seed, step, net, batch, pop))
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 @pytest.mark.parametrize("tag", ["l5", "l7"])
 def test_loss_and_gradients(tag, prec):
     g = load_gold("train_small")
@@ -128,7 +128,7 @@ def test_optimiser_kernel_on_reference_gradients(tag, optname):
     assert np.abs(p1 - ref).max() <= 2 * np.spacing(np.abs(ref).max().astype(np.float32))
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 @pytest.mark.parametrize("optname", ["Adamax", "Adam", "SGD"])
 def test_four_training_steps_replayed_indices(optname, prec):
     g = load_gold("train_small")
@@ -175,7 +175,7 @@ def test_inverse_normalisation_and_truncating_cast_are_bit_exact():
         grp.close()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 def test_config1_decompress_of_reference_parameters(prec):
     g, vol = load_gold("config1_200"), load_gold("brain64")["volume"]
     kw = NETS["c1"]
@@ -196,7 +196,7 @@ def test_config1_decompress_of_reference_parameters(prec):
     assert abs(O.cal_ssim(a, dec[..., None].astype(np.float32), 65535) - float(g["ssim"])) < 0.002
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 def test_config1_200_steps_match_reference_quality(prec):
     """SingleTask default.yaml: 200 full-batch Adamax steps on the shipped 64^3 block (loop enqueued from C)."""
     g, vol = load_gold("config1_200"), load_gold("brain64")["volume"]
@@ -214,7 +214,7 @@ def test_config1_200_steps_match_reference_quality(prec):
     assert abs(O.cal_ssim(a, dec.astype(np.float32), 65535) - float(g["ssim"])) < 0.002
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 def test_networks_in_a_group_are_independent(prec):
     """Blocks are independent networks: a network's losses, parameters and decoded block are bit-identical
     whether it is fitted alone or next to others (the property multi-GPU sharding relies on)."""
@@ -252,7 +252,7 @@ def test_networks_in_a_group_are_independent(prec):
         assert d_one[0].tobytes() == d_all[i].tobytes()
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 def test_full_size_block_properties(prec):
     """At BASELINE size (vessel block 64x256x256, L=7 f=56, batch 100000): decompress is deterministic, agrees
     with forward() on the same coordinates, and the on-device sampler's fit lowers the loss."""
