@@ -52,7 +52,6 @@ int fail(int code, const char* fmt, ...) {
 constexpr size_t kSmemLimit = 200 * 1024;       // dynamic smem budget of the fp32 kernels
 constexpr size_t kPartialCapBytes = 16u << 20;  // gradient-partial budget per network
 constexpr int kTcTile = 128;                    // samples per tcgen05 tile (UMMA M)
-constexpr int kTcCtasPerSm = 1;                 // the fit kernel keeps one CTA per SM (shared memory bound)
 constexpr int kTcEvalTilesPerBlock = 64;
 constexpr int kBuckets = 9;  // F_PAD / 16 in 1..8
 
@@ -240,15 +239,18 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   }
   g->simt_fit_tm = tm;
   g->simt_fit_smem = 0;
-  // tensor-core networks: one CTA per slice, slices sized so that all networks together fill one wave of CTAs
-  long long tc_tiles = 0;
+  // tensor-core networks: one CTA per slice; each width bucket is its own launch, so its slices are sized to fill
+  // one wave of CTAs (SMs x resident CTAs of that bucket's kernel) by themselves
+  long long tc_tiles[kBuckets] = {0}, tc_tps[kBuckets] = {0};
   for (auto& n : g->nets)
     if (n.prec == BRIEF_PREC_F16) {
       const long long b = n.mode == BRIEF_SAMPLE_FULL_BLOCK ? n.n_vox : (long long)n.batch;
-      tc_tiles += (b + kTcTile - 1) / kTcTile;
+      tc_tiles[n.F_PAD / 16] += (b + kTcTile - 1) / kTcTile;
     }
-  const long long tc_wave = (long long)g->num_sms * kTcCtasPerSm;
-  const long long tc_tps = std::max<long long>(1, (tc_tiles + tc_wave - 1) / tc_wave);
+  for (int b = 1; b < kBuckets; ++b) {
+    const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(16 * b);
+    tc_tps[b] = std::max<long long>(1, (tc_tiles[b] + wave - 1) / wave);
+  }
   long long slice_total = 0, part_total = 0, idx_total = 0;
   std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets], op{0}, on;
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
@@ -267,7 +269,7 @@ int finalize(BriefGroup* g, cudaStream_t st) {
     const long long n_tiles = ((long long)n.batch + tile - 1) / tile;
     const long long max_slices = std::max<long long>(1, (long long)(kPartialCapBytes / ((size_t)n.P_dev * 4)));
     long long tps = (n_tiles + max_slices - 1) / max_slices;
-    if (tc) tps = std::max<long long>(tps, tc_tps);
+    if (tc) tps = std::max<long long>(tps, tc_tps[n.F_PAD / 16]);
     tps = std::max<long long>(tps, 1);
     n.slice_len = (int)(tps * tile);
     n.n_slices = (int)((n_tiles + tps - 1) / tps);

@@ -41,7 +41,6 @@ namespace brief {
 
 using namespace umma;
 
-constexpr int kTcThreads = 128;
 constexpr int kTile = 128;
 constexpr int kEvalTilesPerBlock = 64;     // must match kTcEvalTilesPerBlock in brief_capi.cu
 constexpr float kGradScale = 1.0f / 256.0f;  // dy' = kGradScale * w * (yhat - y)
@@ -121,17 +120,61 @@ __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_buf, uint32_t b_
 }
 
 // ==================================================================================================================
+// thread mapping shared by both kernels
+// ==================================================================================================================
+// A CTA has 128 * (F/16) threads.  Warp w serves TMEM lane quadrant q = w & 3 (rows 32q .. 32q+31 of the tile, the
+// only lanes tcgen05.ld lets it touch) and column group cg = w >> 2 (columns 16cg .. 16cg+15): every thread owns
+// ONE 16-column chunk of its sample row per layer, so a hidden-layer epilogue is one tcgen05.ld.x16 + 16 sines +
+// two 16-byte operand stores, and an SM holds 4 warps per scheduler for F = 64 instead of 1.
+template <int F>
+struct TcCfg {
+  static constexpr int CW = F / 16;
+  static constexpr int THREADS = 128 * CW;
+  static constexpr int EVAL_MIN_BLOCKS = F >= 48 ? 2 : F == 32 ? 4 : 8;  // ~1024 threads per SM
+  static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : 2;                  // must match fit_ctas_per_sm()
+};
+
+__device__ __forceinline__ void store_chunk16(unsigned char* buf, int r, int cg, const float* v) {
+  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg, kTile)) =
+      make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg + 1, kTile)) =
+      make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+}
+__device__ __forceinline__ void store_chunk16_sat(unsigned char* buf, int r, int cg, const float* v) {
+  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg, kTile)) =
+      make_uint4(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3]), pack_f16x2_sat(v[4], v[5]),
+                 pack_f16x2_sat(v[6], v[7]));
+  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg + 1, kTile)) =
+      make_uint4(pack_f16x2_sat(v[8], v[9]), pack_f16x2_sat(v[10], v[11]), pack_f16x2_sat(v[12], v[13]),
+                 pack_f16x2_sat(v[14], v[15]));
+}
+
+// theta_i = w * z_i + (w * b)_i for the thread's 16 columns
+__device__ __forceinline__ void theta16(const float* z, const float* __restrict__ wb, float w, float* th) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(wb + i);
+    th[i] = fmaf(z[i], w, b4.x); th[i + 1] = fmaf(z[i + 1], w, b4.y);
+    th[i + 2] = fmaf(z[i + 2], w, b4.z); th[i + 3] = fmaf(z[i + 3], w, b4.w);
+  }
+}
+
+// ==================================================================================================================
 // forward / decompress
 // ==================================================================================================================
-template <int F>
-__global__ void __launch_bounds__(kTcThreads) tc_eval_kernel(EvalArgs a) {
+template <int F, bool DUMP>
+__global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) tc_eval_kernel(EvalArgs a) {
+  constexpr int CW = TcCfg<F>::CW;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
   __shared__ __align__(8) uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float4 s_row[kTile];
+  __shared__ float s_y[CW][kTile];
   __shared__ __align__(16) unsigned short s_out[kTile];
 
-  const int t = threadIdx.x, warp = t >> 5;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;
   int net_id;
   long long chunk;
   if (a.single_net >= 0) {
@@ -149,7 +192,7 @@ __global__ void __launch_bounds__(kTcThreads) tc_eval_kernel(EvalArgs a) {
     fence_mbar_init();
   }
   constexpr int TCOLS = tmem_cols_pow2(F);
-  if (warp == 0) tmem_alloc<TCOLS>(&tmem_base_s);
+  if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,22 +210,20 @@ __global__ void __launch_bounds__(kTcThreads) tc_eval_kernel(EvalArgs a) {
     mbar_expect_tx(&bar_w, bytes);
     bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
   }
-  mbar_wait(&bar_w, 0);
-
   const uint32_t tm = tmem_base_s;
-  const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * cg;
   const uint32_t aAct = smem_u32(sAct), aW = smem_u32(sW);
   const long long total = a.coords ? a.n_coords : n.n_vox;
   const long long n_tiles = (total + kTile - 1) / kTile;
-  const long long tile_end = min(n_tiles, (chunk + 1) * (long long)kEvalTilesPerBlock);
+  const long long tile_begin = chunk * kEvalTilesPerBlock;
+  const long long tile_end = min(n_tiles, tile_begin + kEvalTilesPerBlock);
   uint32_t phase = 0;
   const float wh = n.wh;
 
-  for (long long tile = chunk * kEvalTilesPerBlock; tile < tile_end; ++tile) {
-    const long long s = tile * kTile + t;
-    const bool valid = s < total;
+  auto load_row = [&](long long tile) {  // column group 0 fetches the tile's coordinates for everyone
+    const long long s = tile * kTile + r;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-    if (valid) {
+    if (tile < tile_end && s < total) {
       if (a.coords) {
         x0 = a.coords[s * n.in_dim];
         x1 = a.coords[s * n.in_dim + 1];
@@ -191,24 +232,30 @@ __global__ void __launch_bounds__(kTcThreads) tc_eval_kernel(EvalArgs a) {
         brief_coords(n, a.axes, s, x0, x1, x2);
       }
     }
-    // ---- layer 0 on CUDA cores -> fp16 operand rows
+    s_row[r] = make_float4(x0, x1, x2, 0.f);
+  };
+  if (cg == 0) load_row(tile_begin);
+  mbar_wait(&bar_w, 0);
+  __syncthreads();
+
+  for (long long tile = tile_begin; tile < tile_end; ++tile) {
+    const long long s = tile * kTile + r;
+    const bool valid = s < total;
+    const float4 xr = s_row[r];
+    // ---- layer 0 on CUDA cores -> fp16 operand rows (this thread: features 16cg .. 16cg+15)
 #pragma unroll
-    for (int cg = 0; cg < F / 8; ++cg) {
+    for (int h = 0; h < 2; ++h) {
       float z[8];
-      uint4 pk;
-      if (a.layers_out) {
-        pk = first_layer8<true>(s_w0b, cg * 8, x0, x1, x2, n.w0, z);
-        if (valid)
-          for (int i = 0; i < 8; ++i)
-            if (cg * 8 + i < n.f) a.layers_out[s * n.f + cg * 8 + i] = z[i];
-      } else {
-        pk = first_layer8<false>(s_w0b, cg * 8, x0, x1, x2, n.w0, z);
-      }
-      *reinterpret_cast<uint4*>(sAct + chunk_off(t, cg, kTile)) = pk;
+      const uint4 pk = first_layer8<DUMP>(s_w0b, 16 * cg + 8 * h, xr.x, xr.y, xr.z, n.w0, z);
+      if (DUMP && valid)
+        for (int i = 0; i < 8; ++i)
+          if (16 * cg + 8 * h + i < n.f) a.layers_out[s * n.f + 16 * cg + 8 * h + i] = z[i];
+      *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * cg + h, kTile)) = pk;
     }
-    float y = s_bl[0];
+    float ypart = 0.f;
     // ---- hidden layers on the tensor core
     for (int l = 1; l <= NH; ++l) {
+      tc_fence_before();
       fence_async_smem();
       __syncthreads();
       if (t == 0) {
@@ -219,84 +266,72 @@ __global__ void __launch_bounds__(kTcThreads) tc_eval_kernel(EvalArgs a) {
       mbar_wait(&bar_mma, phase);
       phase ^= 1;
       tc_fence_after();
-      const float* wb = s_wb + (l - 1) * F;
-      const bool last = l == NH;
-      float* zdump = a.layers_out ? a.layers_out + (long long)l * total * n.f + s * n.f : nullptr;
-      float v[2][16];
-      tmem_ld16(lane_addr, v[0]);
+      float v[16], th[16];
+      tmem_ld16(my_tmem, v);
+      tmem_ld_wait();
+      theta16(v, s_wb + (l - 1) * F + 16 * cg, wh, th);
+      if (DUMP && valid) {
+        float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
+        for (int i = 0; i < 16; ++i)
+          if (16 * cg + i < n.f) zdump[16 * cg + i] = th[i] / wh;
+      }
 #pragma unroll
-      for (int ci = 0; ci < F / 16; ++ci) {
-        tmem_ld_wait();
-        if (ci + 1 < F / 16) tmem_ld16(lane_addr + (ci + 1) * 16, v[(ci + 1) & 1]);
-        float* vv = v[ci & 1];
-        float act[16];
+      for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
+      if (l < NH) {
+        store_chunk16(sAct, r, cg, v);
+      } else {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(wb + ci * 16 + i);
-          const float th0 = fmaf(vv[i], wh, b4.x), th1 = fmaf(vv[i + 1], wh, b4.y);
-          const float th2 = fmaf(vv[i + 2], wh, b4.z), th3 = fmaf(vv[i + 3], wh, b4.w);
-          if (zdump && valid) {
-            const float th[4] = {th0, th1, th2, th3};
-            for (int j = 0; j < 4; ++j)
-              if (ci * 16 + i + j < n.f) zdump[ci * 16 + i + j] = th[j] / wh;
-          }
-          act[i] = fast_sin(th0); act[i + 1] = fast_sin(th1); act[i + 2] = fast_sin(th2); act[i + 3] = fast_sin(th3);
+          const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
+          ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
+          ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
         }
-        if (!last) {
-          *reinterpret_cast<uint4*>(sAct + chunk_off(t, 2 * ci, kTile)) =
-              make_uint4(pack_f16x2(act[0], act[1]), pack_f16x2(act[2], act[3]), pack_f16x2(act[4], act[5]),
-                         pack_f16x2(act[6], act[7]));
-          *reinterpret_cast<uint4*>(sAct + chunk_off(t, 2 * ci + 1, kTile)) =
-              make_uint4(pack_f16x2(act[8], act[9]), pack_f16x2(act[10], act[11]), pack_f16x2(act[12], act[13]),
-                         pack_f16x2(act[14], act[15]));
-        } else {
+      }
+    }
+    // ---- last layer: fixed-order sum of the column groups' partial dot products, then the output epilogue
+    s_y[cg][r] = ypart;
+    __syncthreads();
+    const bool full = tile * kTile + kTile <= total;
+    if (cg == 0) {
+      float y = s_bl[0];
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + ci * 16 + i);
-            y = fmaf(w4.x, act[i], y); y = fmaf(w4.y, act[i + 1], y);
-            y = fmaf(w4.z, act[i + 2], y); y = fmaf(w4.w, act[i + 3], y);
+      for (int c = 0; c < CW; ++c) y += s_y[c][r];
+      if (a.out_f32) {
+        if (valid) a.out_f32[s] = y;
+      } else {
+        void* dst = a.out_ptrs[net_id];
+        if (a.out_dtype == 2) {
+          if (valid) reinterpret_cast<float*>(dst)[s] = y;
+        } else {  // inverse normalisation + truncating cast
+          const float vden = brief_denorm(n, y);
+          if (a.out_dtype == 1) {
+            if (full) s_out[r] = (unsigned short)(int)vden;
+            else if (valid) reinterpret_cast<unsigned short*>(dst)[s] = (unsigned short)(int)vden;
+          } else {
+            if (full) reinterpret_cast<unsigned char*>(s_out)[r] = (unsigned char)(int)vden;
+            else if (valid) reinterpret_cast<unsigned char*>(dst)[s] = (unsigned char)(int)vden;
           }
         }
       }
-      tc_fence_before();
+      load_row(tile + 1);
     }
-    // ---- epilogue: inverse normalisation + truncating cast + store
-    if (a.out_f32) {
-      if (valid) a.out_f32[s] = y;
-    } else {
+    __syncthreads();
+    // staged tile -> 16-byte vector stores (256 B contiguous for uint16)
+    if (!a.out_f32 && a.out_dtype != 2 && full) {
       void* dst = a.out_ptrs[net_id];
-      if (a.out_dtype == 2) {
-        if (valid) reinterpret_cast<float*>(dst)[s] = y;
-      } else {
-        const float vden = brief_denorm(n, y);
-        const bool full = tile * kTile + kTile <= total;
-        if (a.out_dtype == 1) {
-          if (full) {  // stage the tile's 128 values, 16 threads store 16 B each (256 B contiguous)
-            s_out[t] = (unsigned short)(int)vden;
-            __syncthreads();
-            if (t < 16)
-              reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dst) + tile * kTile)[t] =
-                  reinterpret_cast<const uint4*>(s_out)[t];
-          } else if (valid) {
-            reinterpret_cast<unsigned short*>(dst)[s] = (unsigned short)(int)vden;
-          }
-        } else {
-          if (full) {
-            reinterpret_cast<unsigned char*>(s_out)[t] = (unsigned char)(int)vden;
-            __syncthreads();
-            if (t < 8)
-              reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + tile * kTile)[t] =
-                  reinterpret_cast<const uint4*>(s_out)[t];
-          } else if (valid) {
-            reinterpret_cast<unsigned char*>(dst)[s] = (unsigned char)(int)vden;
-          }
-        }
+      if (a.out_dtype == 1) {
+        if (t < 16)
+          reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dst) + tile * kTile)[t] =
+              reinterpret_cast<const uint4*>(s_out)[t];
+      } else if (t < 8) {
+        reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + tile * kTile)[t] =
+            reinterpret_cast<const uint4*>(s_out)[t];
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<TCOLS>(tm);
+  if (warp == 0) tmem_dealloc(tm, TCOLS);
 }
 
 // ==================================================================================================================
@@ -305,15 +340,22 @@ __global__ void __launch_bounds__(kTcThreads) tc_eval_kernel(EvalArgs a) {
 // shared memory (dynamic):  sDz[2] | sAct[NS] | sX | sDY | image        (NS = L-1 sine layers)
 //   sDz first: the M = 64 dW contractions read 8 feature groups (16 KB) from the start of a dz buffer whatever F is.
 // TMEM columns: Z [0,F) | X [F,2F) | dW_l [2F + (l-1)F, +F) l=1..NH | dW0 [.., +16) | dWlast [.., +16)
+__host__ __device__ constexpr int fit_tmem_cols(int F, int NH) { return tmem_cols_pow2((NH + 2) * F + 32); }
+
 template <int F>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
+  constexpr int CW = TcCfg<F>::CW;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
   __shared__ __align__(8) uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float4 s_row[kTile];
+  __shared__ float s_y[CW][kTile];
+  __shared__ float s_dy[kTile];
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;
   const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
   const int net_id = a.work_net[wi];
   const int slice = blockIdx.x - a.work_prefix[wi];
@@ -323,12 +365,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fit_kernel(FitArgs a) {
     mbar_init(&bar_mma, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  __syncthreads();
+  const NetDev& n = sn;
+  const int NH = n.L - 2, NS = n.L - 1, f = n.f;
+  const int tcols = fit_tmem_cols(F, NH);
+  if (warp == 0) tmem_alloc(&tmem_base_s, tcols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const NetDev& n = sn;
-  const int NH = n.L - 2, NS = n.L - 1, f = n.f;
   constexpr uint32_t BUF = kTile * F * 2;  // one [128 x F] fp16 buffer
   unsigned char* sDz = smem;
   unsigned char* sAct = sDz + 2 * BUF;
@@ -345,13 +389,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fit_kernel(FitArgs a) {
     mbar_expect_tx(&bar_w, bytes);
     bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
   }
-  // second column group of the two 16-column blocks is constant zero
-  *reinterpret_cast<uint4*>(sX + chunk_off(t, 1, kTile)) = make_uint4(0, 0, 0, 0);
-  *reinterpret_cast<uint4*>(sDY + chunk_off(t, 1, kTile)) = make_uint4(0, 0, 0, 0);
-  mbar_wait(&bar_w, 0);
+  if (cg == 0) {  // second column group of the two 16-column blocks is constant zero
+    *reinterpret_cast<uint4*>(sX + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sDY + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
+  }
 
   const uint32_t tm = tmem_base_s;
-  const uint32_t lane_addr = tm + ((uint32_t)(warp * 32) << 16);
+  const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * cg;
   const uint32_t TZ = tm, TX = tm + F, TDW = tm + 2 * F, TDW0 = TDW + NH * F, TDWL = TDW0 + 16;
   const uint32_t aDz = smem_u32(sDz), aAct = smem_u32(sAct), aX = smem_u32(sX), aDY = smem_u32(sDY), aW = smem_u32(sW);
   uint32_t phase = 0;
@@ -361,34 +405,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fit_kernel(FitArgs a) {
   float loss_acc = 0.f;
   int it = 0;
 
-  for (long long tile0 = s_begin; tile0 < s_end; tile0 += kTile, ++it) {
-    const long long s = tile0 + t;
-    const bool valid = s < s_end;
-    float x0 = 0.f, x1 = 0.f, x2 = 0.f, yv = 0.f, wv = 0.f;
-    if (valid) {
+  // the sampler gather for one tile (column group 0): index -> coordinates, normalised target, weight
+  float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f, gy = 0.f, gw = 0.f;
+  auto gather = [&](long long tile0) {
+    const long long s = tile0 + r;
+    gx0 = gx1 = gx2 = gy = gw = 0.f;
+    if (tile0 < s_end && s < s_end) {
       long long idx;
       if (n.mode == 0) idx = s;
       else if (a.idx) idx = a.idx[n.idx_off + s];
       else idx = brief_sample_index(a.seed, a.step, (uint32_t)net_id, (uint64_t)s, (uint64_t)n.n_vox);
-      brief_coords(n, a.axes, idx, x0, x1, x2);
+      brief_coords(n, a.axes, idx, gx0, gx1, gx2);
       const float raw = brief_raw_value(n, idx);
-      yv = brief_normalize(n, raw);
-      wv = brief_weight(n, idx, raw);
+      gy = brief_normalize(n, raw);
+      gw = brief_weight(n, idx, raw);
     }
-    {  // B operand of the dW0 contraction: [x_hi(3), 1, x_lo(3), 0]  (hi/lo split keeps fp32-grade coordinates)
-      const float h0 = __half2float(__float2half_rn(x0)), h1 = __half2float(__float2half_rn(x1)),
-                  h2 = __half2float(__float2half_rn(x2));
-      *reinterpret_cast<uint4*>(sX + chunk_off(t, 0, kTile)) =
-          make_uint4(pack_f16x2(h0, h1), pack_f16x2(h2, 1.0f), pack_f16x2(x0 - h0, x1 - h1), pack_f16x2(x2 - h2, 0.f));
+  };
+  if (cg == 0) gather(s_begin);
+  mbar_wait(&bar_w, 0);
+
+  for (long long tile0 = s_begin; tile0 < s_end; tile0 += kTile, ++it) {
+    const bool valid = tile0 + r < s_end;
+    const float yv = gy, wv = gw;
+    if (cg == 0) {
+      s_row[r] = make_float4(gx0, gx1, gx2, 0.f);
+      // B operand of the dW0 contraction: [x_hi(3), 1, x_lo(3), 0]  (hi/lo split keeps fp32-grade coordinates)
+      const float h0 = __half2float(__float2half_rn(gx0)), h1 = __half2float(__float2half_rn(gx1)),
+                  h2 = __half2float(__float2half_rn(gx2));
+      *reinterpret_cast<uint4*>(sX + chunk_off(r, 0, kTile)) =
+          make_uint4(pack_f16x2(h0, h1), pack_f16x2(h2, 1.0f), pack_f16x2(gx0 - h0, gx1 - h1), pack_f16x2(gx2 - h2, 0.f));
     }
-    // ---- forward, layer 0 (CUDA cores)
+    __syncthreads();
+    const float4 xr = s_row[r];
+    // ---- forward, layer 0 (CUDA cores): features 16cg .. 16cg+15
 #pragma unroll
-    for (int cg = 0; cg < F / 8; ++cg) {
+    for (int h = 0; h < 2; ++h) {
       float z[8];
-      *reinterpret_cast<uint4*>(sAct + chunk_off(t, cg, kTile)) = first_layer8<false>(s_w0b, cg * 8, x0, x1, x2, w0, z);
+      *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * cg + h, kTile)) =
+          first_layer8<false>(s_w0b, 16 * cg + 8 * h, xr.x, xr.y, xr.z, w0, z);
     }
     // ---- forward, hidden layers (tensor core); a_l -> sAct[l]
-    float y = s_bl[0];
+    float th[16];
+    float ypart = 0.f;
     for (int l = 1; l <= NH; ++l) {
       tc_fence_before();
       fence_async_smem();
@@ -401,75 +459,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fit_kernel(FitArgs a) {
       mbar_wait(&bar_mma, phase);
       phase ^= 1;
       tc_fence_after();
-      const float* wb = s_wb + (l - 1) * F;
-      unsigned char* dstA = sAct + (size_t)l * BUF;
-      const bool last = l == NH;
-      float v[2][16];
-      tmem_ld16(lane_addr, v[0]);
+      float v[16];
+      tmem_ld16(my_tmem, v);
+      tmem_ld_wait();
+      theta16(v, s_wb + (l - 1) * F + 16 * cg, wh, th);
 #pragma unroll
-      for (int ci = 0; ci < F / 16; ++ci) {
-        tmem_ld_wait();
-        if (ci + 1 < F / 16) tmem_ld16(lane_addr + (ci + 1) * 16, v[(ci + 1) & 1]);
-        float* vv = v[ci & 1];
-        float act[16];
+      for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
+      store_chunk16(sAct + (size_t)l * BUF, r, cg, v);
+      if (l == NH) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(wb + ci * 16 + i);
-          act[i] = fast_sin(fmaf(vv[i], wh, b4.x)); act[i + 1] = fast_sin(fmaf(vv[i + 1], wh, b4.y));
-          act[i + 2] = fast_sin(fmaf(vv[i + 2], wh, b4.z)); act[i + 3] = fast_sin(fmaf(vv[i + 3], wh, b4.w));
-        }
-        *reinterpret_cast<uint4*>(dstA + chunk_off(t, 2 * ci, kTile)) =
-            make_uint4(pack_f16x2(act[0], act[1]), pack_f16x2(act[2], act[3]), pack_f16x2(act[4], act[5]),
-                       pack_f16x2(act[6], act[7]));
-        *reinterpret_cast<uint4*>(dstA + chunk_off(t, 2 * ci + 1, kTile)) =
-            make_uint4(pack_f16x2(act[8], act[9]), pack_f16x2(act[10], act[11]), pack_f16x2(act[12], act[13]),
-                       pack_f16x2(act[14], act[15]));
-        if (last) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + ci * 16 + i);
-            y = fmaf(w4.x, act[i], y); y = fmaf(w4.y, act[i + 1], y);
-            y = fmaf(w4.z, act[i + 2], y); y = fmaf(w4.w, act[i + 3], y);
-          }
+          const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
+          ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
+          ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
         }
       }
     }
-    // ---- loss (datal2, main.py:176-182) and scaled output gradient
-    float dys = 0.f;
-    if (valid) {
-      const float e = y - yv;
-      const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : wv;
-      loss_acc = fmaf(wt * e, e, loss_acc);
-      dys = kGradScale * wt * e;
-    }
-    *reinterpret_cast<uint4*>(sDY + chunk_off(t, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
-    // dz_NH = dy * Wlast * w * cos(w z_NH): second pass over the accumulator that is still in TMEM
-    {
-      const float* wb = s_wb + (NH - 1) * F;
-      float v[2][16];
-      tmem_ld16(lane_addr, v[0]);
+    // ---- loss (datal2, main.py:176-182) and the scaled output gradient
+    s_y[cg][r] = ypart;
+    __syncthreads();
+    if (cg == 0) {
+      float y = s_bl[0];
 #pragma unroll
-      for (int ci = 0; ci < F / 16; ++ci) {
-        tmem_ld_wait();
-        if (ci + 1 < F / 16) tmem_ld16(lane_addr + (ci + 1) * 16, v[(ci + 1) & 1]);
-        float* vv = v[ci & 1];
-        float dz[16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(wb + ci * 16 + i);
-          const float4 w4 = *reinterpret_cast<const float4*>(s_wl + ci * 16 + i);
-          dz[i] = dys * w4.x * wh * fast_cos(fmaf(vv[i], wh, b4.x));
-          dz[i + 1] = dys * w4.y * wh * fast_cos(fmaf(vv[i + 1], wh, b4.y));
-          dz[i + 2] = dys * w4.z * wh * fast_cos(fmaf(vv[i + 2], wh, b4.z));
-          dz[i + 3] = dys * w4.w * wh * fast_cos(fmaf(vv[i + 3], wh, b4.w));
-        }
-        *reinterpret_cast<uint4*>(sDz + chunk_off(t, 2 * ci, kTile)) =
-            make_uint4(pack_f16x2_sat(dz[0], dz[1]), pack_f16x2_sat(dz[2], dz[3]), pack_f16x2_sat(dz[4], dz[5]),
-                       pack_f16x2_sat(dz[6], dz[7]));
-        *reinterpret_cast<uint4*>(sDz + chunk_off(t, 2 * ci + 1, kTile)) =
-            make_uint4(pack_f16x2_sat(dz[8], dz[9]), pack_f16x2_sat(dz[10], dz[11]), pack_f16x2_sat(dz[12], dz[13]),
-                       pack_f16x2_sat(dz[14], dz[15]));
+      for (int c = 0; c < CW; ++c) y += s_y[c][r];
+      float dys = 0.f;
+      if (valid) {
+        const float e = y - yv;
+        const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : wv;
+        loss_acc = fmaf(wt * e, e, loss_acc);
+        dys = kGradScale * wt * e;
       }
+      s_dy[r] = dys;
+      *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
+      gather(tile0 + kTile);  // prefetch the next tile's samples; consumed at the top of the next iteration
+    }
+    __syncthreads();
+    {  // dz_NH = dy * Wlast * w * cos(w z_NH) from the sine arguments still in registers
+      const float dys = s_dy[r];
+      float dz[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
+        dz[i] = dys * w4.x * wh * fast_cos(th[i]); dz[i + 1] = dys * w4.y * wh * fast_cos(th[i + 1]);
+        dz[i + 2] = dys * w4.z * wh * fast_cos(th[i + 2]); dz[i + 3] = dys * w4.w * wh * fast_cos(th[i + 3]);
+      }
+      store_chunk16_sat(sDz, r, cg, dz);
     }
     // ---- backward through the hidden layers
     int cur = 0;
@@ -480,62 +514,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fit_kernel(FitArgs a) {
       if (t == 0) {
         tc_fence_after();
         const uint32_t dzb = aDz + (uint32_t)cur * BUF;
-        if (l == NH) issue_dw<16>(TDWL, aAct + (uint32_t)NH * BUF, aDY, it > 0);       // dWlast, dblast
-        issue_dw<F>(TDW + (uint32_t)(l - 1) * F, dzb, aAct + (uint32_t)(l - 1) * BUF, it > 0);  // dW_l, db_l
-        if (l >= 2) issue_forward<F>(TZ, aAct + (uint32_t)(l - 2) * BUF, aW + (uint32_t)(l - 2) * F * F * 2);  // z_{l-1}
-        issue_dx<F>(TX, dzb, aW + (uint32_t)(l - 1) * F * F * 2);                      // dX_{l-1}
+        // what the epilogue waits for: z_{l-1} (recomputed) and dX_{l-1}
+        if (l >= 2) issue_forward<F>(TZ, aAct + (uint32_t)(l - 2) * BUF, aW + (uint32_t)(l - 2) * F * F * 2);
+        issue_dx<F>(TX, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
         commit(&bar_mma);
+        // off the critical path (tracked by the next commit): dW_l, db_l (+ dWlast, dblast)
+        issue_dw<F>(TDW + (uint32_t)(l - 1) * F, dzb, aAct + (uint32_t)(l - 1) * BUF, it > 0);
+        if (l == NH) issue_dw<16>(TDWL, aAct + (uint32_t)NH * BUF, aDY, it > 0);
       }
       mbar_wait(&bar_mma, phase);
       phase ^= 1;
       tc_fence_after();
-      unsigned char* dstZ = sDz + (size_t)(cur ^ 1) * BUF;
+      float vx[16], dz[16];
       if (l >= 2) {
-        const float* wb = s_wb + (l - 2) * F;
-        float vz[16], vx[16];
+        float vz[16];
+        tmem_ld16(my_tmem, vz);
+        tmem_ld16(my_tmem + F, vx);
+        tmem_ld_wait();
+        theta16(vz, s_wb + (l - 2) * F + 16 * cg, wh, dz);
 #pragma unroll
-        for (int ci = 0; ci < F / 16; ++ci) {
-          tmem_ld16(lane_addr + ci * 16, vz);
-          tmem_ld16(lane_addr + F + ci * 16, vx);
-          tmem_ld_wait();
-          float dz[16];
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(wb + ci * 16 + i);
-            dz[i] = vx[i] * wh * fast_cos(fmaf(vz[i], wh, b4.x));
-            dz[i + 1] = vx[i + 1] * wh * fast_cos(fmaf(vz[i + 1], wh, b4.y));
-            dz[i + 2] = vx[i + 2] * wh * fast_cos(fmaf(vz[i + 2], wh, b4.z));
-            dz[i + 3] = vx[i + 3] * wh * fast_cos(fmaf(vz[i + 3], wh, b4.w));
-          }
-          *reinterpret_cast<uint4*>(dstZ + chunk_off(t, 2 * ci, kTile)) =
-              make_uint4(pack_f16x2_sat(dz[0], dz[1]), pack_f16x2_sat(dz[2], dz[3]), pack_f16x2_sat(dz[4], dz[5]),
-                         pack_f16x2_sat(dz[6], dz[7]));
-          *reinterpret_cast<uint4*>(dstZ + chunk_off(t, 2 * ci + 1, kTile)) =
-              make_uint4(pack_f16x2_sat(dz[8], dz[9]), pack_f16x2_sat(dz[10], dz[11]), pack_f16x2_sat(dz[12], dz[13]),
-                         pack_f16x2_sat(dz[14], dz[15]));
-        }
+        for (int i = 0; i < 16; ++i) dz[i] = vx[i] * wh * fast_cos(dz[i]);
       } else {  // l == 1: dz_0 = dX_0 * w0 * cos(w0 z_0), z_0 recomputed on CUDA cores
-        float vx[16];
+        tmem_ld16(my_tmem + F, vx);
+        tmem_ld_wait();
 #pragma unroll
-        for (int ci = 0; ci < F / 16; ++ci) {
-          tmem_ld16(lane_addr + F + ci * 16, vx);
-          tmem_ld_wait();
-          float dz[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 w = s_w0b[ci * 16 + i];
-            float z = w.w;
-            z = fmaf(w.x, x0, z); z = fmaf(w.y, x1, z); z = fmaf(w.z, x2, z);
-            dz[i] = vx[i] * w0 * fast_cos(w0 * z);
-          }
-          *reinterpret_cast<uint4*>(dstZ + chunk_off(t, 2 * ci, kTile)) =
-              make_uint4(pack_f16x2_sat(dz[0], dz[1]), pack_f16x2_sat(dz[2], dz[3]), pack_f16x2_sat(dz[4], dz[5]),
-                         pack_f16x2_sat(dz[6], dz[7]));
-          *reinterpret_cast<uint4*>(dstZ + chunk_off(t, 2 * ci + 1, kTile)) =
-              make_uint4(pack_f16x2_sat(dz[8], dz[9]), pack_f16x2_sat(dz[10], dz[11]), pack_f16x2_sat(dz[12], dz[13]),
-                         pack_f16x2_sat(dz[14], dz[15]));
+        for (int i = 0; i < 16; ++i) {
+          const float4 w = s_w0b[16 * cg + i];
+          float z = w.w;
+          z = fmaf(w.x, xr.x, z); z = fmaf(w.y, xr.y, z); z = fmaf(w.z, xr.z, z);
+          dz[i] = vx[i] * w0 * fast_cos(w0 * z);
         }
       }
+      store_chunk16_sat(sDz + (size_t)(cur ^ 1) * BUF, r, cg, dz);
       cur ^= 1;
     }
     // ---- dW0 += dz_0^T [x_hi, 1, x_lo]; wait so that the next tile may overwrite sX / sDz / sAct
@@ -554,58 +564,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_fit_kernel(FitArgs a) {
 
   // ---- slice epilogue: loss partial + gradient partials (TMEM -> global), scale removed in fp32
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
+  if (cg == 0) {
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
-  if (lane == 0) s_red[warp] = loss_acc;
+    for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
+    if (lane == 0) s_red[q] = loss_acc;
+  }
   float* part = a.partials + n.part_off + (long long)slice * n.P_dev;
-  for (int i = t; i < n.P_dev; i += kTcThreads) part[i] = 0.f;
+  for (int i = t; i < n.P_dev; i += TcCfg<F>::THREADS) part[i] = 0.f;
   __syncthreads();
   if (t == 0) a.loss_partials[n.slice_off + slice] = (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]) * inv_count;
   if (it > 0) {
     const float unscale = 2.0f * inv_count / kGradScale;
-    const int o = warp * 16 + lane;  // accumulator row held by this thread (M = 64 layout: lanes 0..15 of each warp)
+    const int o = q * 16 + lane;  // accumulator row held by this thread (M = 64 layout: lanes 0..15 of each quadrant)
     const bool row_ok = lane < 16 && o < F;
     const int F4 = n.F4;
     float v[16];
     for (int l = 1; l <= NH; ++l) {
+      tmem_ld16(my_tmem + 2 * F + (l - 1) * F, v);
+      tmem_ld_wait();
+      if (row_ok && o < f) {
 #pragma unroll
-      for (int ci = 0; ci < F / 16; ++ci) {
-        tmem_ld16(lane_addr + 2 * F + (l - 1) * F + ci * 16, v);
-        tmem_ld_wait();
-        if (row_ok && o < f) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k = ci * 16 + i;
-            if (k < f) part[dl_W(n, l) + o * F4 + k] = v[i] * unscale;
-            else if (k == f) part[dl_b(n, l) + o] = v[i] * unscale;
-          }
+        for (int i = 0; i < 16; ++i) {
+          const int k = 16 * cg + i;
+          if (k < f) part[dl_W(n, l) + o * F4 + k] = v[i] * unscale;
+          else if (k == f) part[dl_b(n, l) + o] = v[i] * unscale;
         }
       }
     }
-    tmem_ld16(lane_addr + 2 * F + NH * F, v);  // dW0 block
-    tmem_ld_wait();
-    if (row_ok && o < f) {
-      part[dl_W0(n) + 4 * o + 0] = (v[0] + v[4]) * unscale;
-      part[dl_W0(n) + 4 * o + 1] = (v[1] + v[5]) * unscale;
-      if (n.in_dim == 3) part[dl_W0(n) + 4 * o + 2] = (v[2] + v[6]) * unscale;
-      part[dl_b0(n) + o] = v[3] * unscale;
-    }
-    tmem_ld16(lane_addr + 2 * F + NH * F + 16, v);  // dWlast block: row = feature of a_NH, column 0
-    tmem_ld_wait();
-    if (row_ok) {
-      if (o < f) part[dl_Wlast(n) + o] = v[0] * unscale;
-      else if (o == f) part[dl_blast(n)] = v[0] * unscale;
+    if (cg == 0) {
+      tmem_ld16(my_tmem + 2 * F + NH * F, v);  // dW0 block
+      tmem_ld_wait();
+      if (row_ok && o < f) {
+        part[dl_W0(n) + 4 * o + 0] = (v[0] + v[4]) * unscale;
+        part[dl_W0(n) + 4 * o + 1] = (v[1] + v[5]) * unscale;
+        if (n.in_dim == 3) part[dl_W0(n) + 4 * o + 2] = (v[2] + v[6]) * unscale;
+        part[dl_b0(n) + o] = v[3] * unscale;
+      }
+      tmem_ld16(my_tmem + 2 * F + NH * F + 16, v);  // dWlast block: row = feature of a_NH, column 0
+      tmem_ld_wait();
+      if (row_ok) {
+        if (o < f) part[dl_Wlast(n) + o] = v[0] * unscale;
+        else if (o == f) part[dl_blast(n)] = v[0] * unscale;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tm);
+  if (warp == 0) tmem_dealloc(tm, tcols);
 }
 
 // ==================================================================================================================
 // host side
 // ==================================================================================================================
 int tc_fpad(int f) { return ((f + 1 + 15) / 16) * 16; }
+int tc_fit_ctas_per_sm(int F) { return F >= 48 ? 1 : 2; }  // == TcCfg<F>::FIT_MIN_BLOCKS
 size_t tc_wpack_bytes(int F, int L) { return img_bytes(F, L - 2); }
 size_t tc_eval_smem(int F, int L) { return img_bytes_padded(F, L - 2) + (size_t)kTile * F * 2; }
 size_t tc_fit_smem(int F, int L) {
@@ -624,9 +636,16 @@ bool tc_supported(int f, int L, int in_dim, int out_dim) {
 template <int F>
 static cudaError_t launch_eval_f(const EvalArgs& a, int L_max, int n_blocks, cudaStream_t st) {
   const size_t smem = tc_eval_smem(F, L_max);
-  cudaError_t e = cudaFuncSetAttribute(tc_eval_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  tc_eval_kernel<F><<<n_blocks, kTcThreads, smem, st>>>(a);
+  cudaError_t e;
+  if (a.layers_out) {
+    e = cudaFuncSetAttribute(tc_eval_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tc_eval_kernel<F, true><<<n_blocks, TcCfg<F>::THREADS, smem, st>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(tc_eval_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tc_eval_kernel<F, false><<<n_blocks, TcCfg<F>::THREADS, smem, st>>>(a);
+  }
   return cudaGetLastError();
 }
 
@@ -646,7 +665,7 @@ static cudaError_t launch_fit_f(const FitArgs& a, int L_max, int n_blocks, cudaS
   const size_t smem = tc_fit_smem(F, L_max) < 49152 ? 49152 : tc_fit_smem(F, L_max);
   cudaError_t e = cudaFuncSetAttribute(tc_fit_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fit_kernel<F><<<n_blocks, kTcThreads, smem, st>>>(a);
+  tc_fit_kernel<F><<<n_blocks, TcCfg<F>::THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128) probe(const float* A_in, const float* W_i
     if (bfmt == 0) *reinterpret_cast<__half*>(p) = __float2half(W_in[t * F + c]); else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16(W_in[t * F + c]);
   }
   if (t == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc<64>(&tmem_base);
+  if (warp == 0) tmem_alloc(&tmem_base, 64);
   fence_async_smem(); tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tm = tmem_base;
   if (t == 0) {
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(128) probe(const float* A_in, const float* W_i
     for (int i = 0; i < 16; ++i) D[t * F + c0 + i] = v[i];
   }
   tc_fence_before(); __syncthreads();
-  if (warp == 0) tmem_dealloc<64>(tm);
+  if (warp == 0) tmem_dealloc(tm, 64);
 }
 int main() {
   std::vector<float> A(128 * F), W(F * F), d(128 * F);

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128) probe(const float* A_in, const float* G_i
     for (int c = 0; c < F; ++c)
       *reinterpret_cast<__nv_bfloat16*>(sW + chunk_off(t, c >> 3, F) + (c & 7) * 2) = __float2bfloat16(W_in[t * F + c]);
   if (t == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc<512>(&tmem_base);
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) probe(const float* A_in, const float* G_i
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tm);
+  if (warp == 0) tmem_dealloc(tm, 512);
 }
 
 template <int F>
