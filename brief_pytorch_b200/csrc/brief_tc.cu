@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) 
       tc_fence_before();
       fence_async_smem();
       __syncthreads();
-      if (t == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         issue_forward<F>(tm, aAct, aW + (uint32_t)(l - 1) * F * F * 2);
         commit(&bar_mma);
@@ -341,6 +341,15 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) 
 //   sDz first: the M = 64 dW contractions read 8 feature groups (16 KB) from the start of a dz buffer whatever F is.
 // TMEM columns: Z [0,F) | X [F,2F) | dW_l [2F + (l-1)F, +F) l=1..NH | dW0 [.., +16) | dWlast [.., +16)
 __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) { return tmem_cols_pow2((NH + 2) * F + 32); }
+
+#ifdef BRIEF_TC_TIMING
+__device__ unsigned long long g_tc_timing[16];
+#define TT(var) const long long var = clock64()
+#define TACC(slot, expr) if (blockIdx.x == 0 && (t == 0 || t == TcCfg<F>::THREADS - 1)) atomicAdd(&g_tc_timing[(slot) + (t == 0 ? 0 : 8)], (unsigned long long)(expr))
+#else
+#define TT(var)
+#define TACC(slot, expr)
+#endif
 
 template <int F>
 __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
@@ -425,6 +434,7 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
   mbar_wait(&bar_w, 0);
 
   for (long long tile0 = s_begin; tile0 < s_end; tile0 += kTile, ++it) {
+    TT(ctile);
     const bool valid = tile0 + r < s_end;
     const float yv = gy, wv = gw;
     if (cg == 0) {
@@ -448,24 +458,32 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
     float th[16];
     float ypart = 0.f;
     for (int l = 1; l <= NH; ++l) {
+      TT(c0);
       tc_fence_before();
       fence_async_smem();
+      TT(c1);
       __syncthreads();
-      if (t == 0) {
+      TT(c2);
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         issue_forward<F>(TZ, aAct + (uint32_t)(l - 1) * BUF, aW + (uint32_t)(l - 1) * F * F * 2);
         commit(&bar_mma);
       }
+      TT(c3);
       mbar_wait(&bar_mma, phase);
+      TT(c4);
       phase ^= 1;
       tc_fence_after();
       float v[16];
       tmem_ld16(my_tmem, v);
       tmem_ld_wait();
+      TT(c5);
+      TACC(0, c1 - c0); TACC(1, c2 - c1); TACC(2, c3 - c2); TACC(3, c4 - c3); TACC(4, c5 - c4);
       theta16(v, s_wb + (l - 1) * F + 16 * cg, wh, th);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
       store_chunk16(sAct + (size_t)l * BUF, r, cg, v);
+      { TT(c6); TACC(5, c6 - c5); }
       if (l == NH) {
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
@@ -511,7 +529,7 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
       tc_fence_before();
       fence_async_smem();
       __syncthreads();
-      if (t == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         const uint32_t dzb = aDz + (uint32_t)cur * BUF;
         // what the epilogue waits for: z_{l-1} (recomputed) and dX_{l-1}
@@ -552,7 +570,7 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
     tc_fence_before();
     fence_async_smem();
     __syncthreads();
-    if (t == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_dw<16>(TDW0, aDz + (uint32_t)cur * BUF, aX, it > 0);
       commit(&bar_mma);
@@ -560,6 +578,7 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
     mbar_wait(&bar_mma, phase);
     phase ^= 1;
     tc_fence_after();
+    { TT(cend); TACC(6, cend - ctile); TACC(7, 1); }
   }
 
   // ---- slice epilogue: loss partial + gradient partials (TMEM -> global), scale removed in fp32
@@ -680,3 +699,11 @@ cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int L_max, int n_blocks, 
 }
 
 }  // namespace brief
+
+#ifdef BRIEF_TC_TIMING
+extern "C" int brief_debug_read_timing(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, brief::g_tc_timing, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(brief::g_tc_timing, z, sizeof z); }
+  return 0;
+}
+#endif

@@ -80,6 +80,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// one lane of a fully converged warp.  MMA issue must sit behind elect.sync inside a WARP-UNIFORM branch: behind a
+// thread-index test (`if (threadIdx.x == 0)`) the compiler cannot prove the descriptors uniform and wraps every
+// tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~90 cycles per instruction, measured).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- fences -----------------------------------------------------------------------------------------------------
 // generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
