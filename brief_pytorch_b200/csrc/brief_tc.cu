@@ -129,7 +129,8 @@ __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_buf, uint32_t b_
 template <int F>
 struct TcCfg {
   static constexpr int CW = F / 16;
-  static constexpr int THREADS = 128 * CW;
+  static constexpr int THREADS = 128 * CW;                                // epilogue threads
+  static constexpr int FIT_THREADS = THREADS + 32;                        // + one warp that only issues MMAs
   static constexpr int EVAL_MIN_BLOCKS = F >= 48 ? 2 : F == 32 ? 4 : 8;  // ~1024 threads per SM
   static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : 2;                  // must match fit_ctas_per_sm()
 };
@@ -337,26 +338,38 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) 
 // ==================================================================================================================
 // fit: gather + forward + weighted L2 + backward -> per-slice gradient partials
 // ==================================================================================================================
-// shared memory (dynamic):  sDz[2] | sAct[NS] | sX | sDY | image        (NS = L-1 sine layers)
-//   sDz first: the M = 64 dW contractions read 8 feature groups (16 KB) from the start of a dz buffer whatever F is.
-// TMEM columns: Z [0,F) | X [F,2F) | dW_l [2F + (l-1)F, +F) l=1..NH | dW0 [.., +16) | dWlast [.., +16)
-__host__ __device__ constexpr int fit_tmem_cols(int F, int NH) { return tmem_cols_pow2((NH + 2) * F + 32); }
-
-#ifdef BRIEF_TC_TIMING
-__device__ unsigned long long g_tc_timing[16];
-#define TT(var) const long long var = clock64()
-#define TACC(slot, expr) if (blockIdx.x == 0 && (t == 0 || t == TcCfg<F>::THREADS - 1)) atomicAdd(&g_tc_timing[(slot) + (t == 0 ? 0 : 8)], (unsigned long long)(expr))
-#else
-#define TT(var)
-#define TACC(slot, expr)
-#endif
+// TWO tiles are in flight per CTA, in opposite phases: while tile A walks backward through the layers, tile B (the
+// next 128 samples) walks forward.  The same 128*(F/16) threads alternate between them, so every tensor-core phase
+// (MMA issue + execution + commit latency, ~450-750 cycles, measured) runs underneath the other tile's epilogue:
+//
+//     wait A  ->  epilogue A (dz_{l-1})  ->  signal  ->  wait B  ->  epilogue B (a_j)  ->  signal  -> ...
+//
+// A tcgen05.mma blocks the issuing thread for about as long as it executes (measured: ~62 cycles per 128x64x16
+// instruction, tests/cuda/umma_timing_probe.cu), so MMAs are issued by a DEDICATED extra warp that mirrors the
+// schedule and is told through mbarriers (one arrival per epilogue warp) when a tile's operands are in place;
+// the epilogue warps never wait for an issue, only for the commit of the MMAs they consume.
+//
+// Both tiles' activations fit because their lifetimes are complementary: backward stage l of A still needs
+// a_0..a_{l-1} while forward stage j = NH+1-l of B has produced a_0..a_j.  Even tiles keep layer j in ring slot j,
+// odd tiles in slot R-1-j (R = NS + 2 slots), so a forward write only ever lands in a slot the backward tile has
+// finished with (the wait on A's barrier that precedes B's epilogue also covers A's trailing dW MMAs).
+//
+// shared memory (dynamic):  sDz[2] | ring[R] | sX[2] | sDY | image          (NS = L-1 sine layers, R = NS + 2)
+//   sDz first: the M = 64 dW contractions read 8 feature groups (16 KB) from the start of a buffer whatever F is.
+// TMEM columns: Zf [0,F) forward z | Zb [F,2F) recomputed z | Xb [2F,3F) dX | accumulators from 3F:
+//   accumulator i (M = 64: 16 lanes per quadrant) lives in column block i/2, lane half i%2 — two per block.
+//   i = 0..NH-1: dW_{i+1} (F columns; column f = db), i = NH: dW0 block (16 columns), i = NH+1: dWlast block.
+__host__ __device__ constexpr int fit_acc_blocks(int NH) { return (NH + 2 + 1) / 2; }
+__host__ __device__ constexpr int fit_tmem_cols(int F, int NH) { return tmem_cols_pow2(3 * F + fit_acc_blocks(NH) * F); }
 
 template <int F>
-__global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
   constexpr int CW = TcCfg<F>::CW;
+  constexpr int NT = TcCfg<F>::THREADS;   // epilogue threads; warp NT/32 is the MMA warp
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float4 s_row[kTile];
   __shared__ float s_y[CW][kTile];
@@ -364,30 +377,35 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;
+  const bool mma_warp = warp == NW;
+  const int q = warp & 3, cg = mma_warp ? CW : (warp >> 2), r = 32 * q + lane;
   const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
   const int net_id = a.work_net[wi];
   const int slice = blockIdx.x - a.work_prefix[wi];
   tc_load_net(sn, a.nets[net_id]);
   if (t == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_a, 1);
+    mbar_init(&bar_b, 1);
+    mbar_init(&bar_ra, NW);  // "operands of the backward tile are in place": one arrival per epilogue warp
+    mbar_init(&bar_rb, NW);  // same for the forward tile
     fence_mbar_init();
   }
   __syncthreads();
   const NetDev& n = sn;
-  const int NH = n.L - 2, NS = n.L - 1, f = n.f;
+  const int NH = n.L - 2, NS = n.L - 1, f = n.f, R = NS + 2;
   const int tcols = fit_tmem_cols(F, NH);
   if (warp == 0) tmem_alloc(&tmem_base_s, tcols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  constexpr uint32_t BUF = kTile * F * 2;  // one [128 x F] fp16 buffer
+  constexpr uint32_t BUF = kTile * F * 2;    // one [128 x F] fp16 buffer
+  constexpr uint32_t BLK = kTile * 16 * 2;   // one [128 x 16] fp16 block
   unsigned char* sDz = smem;
-  unsigned char* sAct = sDz + 2 * BUF;
-  unsigned char* sX = sAct + (size_t)NS * BUF;
-  unsigned char* sDY = sX + kTile * 16 * 2;
-  unsigned char* sW = sDY + kTile * 16 * 2;
+  unsigned char* sRing = sDz + 2 * BUF;
+  unsigned char* sX = sRing + (size_t)R * BUF;
+  unsigned char* sDY = sX + 2 * BLK;
+  unsigned char* sW = sDY + BLK;
   const float* side = reinterpret_cast<const float*>(sW + img_hidden_bytes(F, NH));
   const float4* s_w0b = reinterpret_cast<const float4*>(side);
   const float* s_wb = side + 4 * F;
@@ -398,28 +416,31 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
     mbar_expect_tx(&bar_w, bytes);
     bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
   }
-  if (cg == 0) {  // second column group of the two 16-column blocks is constant zero
+  if (cg == 0) {  // second column group of the 16-column blocks is constant zero
     *reinterpret_cast<uint4*>(sX + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sX + BLK + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<uint4*>(sDY + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
   }
 
   const uint32_t tm = tmem_base_s;
   const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * cg;
-  const uint32_t TZ = tm, TX = tm + F, TDW = tm + 2 * F, TDW0 = TDW + NH * F, TDWL = TDW0 + 16;
-  const uint32_t aDz = smem_u32(sDz), aAct = smem_u32(sAct), aX = smem_u32(sX), aDY = smem_u32(sDY), aW = smem_u32(sW);
-  uint32_t phase = 0;
+  const uint32_t TZF = tm, TZB = tm + F, TXB = tm + 2 * F;
+  auto acc_addr = [&](int i) { return tm + 3 * F + (uint32_t)(i >> 1) * F + ((uint32_t)(i & 1) << 20); };  // lane 16 = 16 << 16
+  const uint32_t aDz = smem_u32(sDz), aRing = smem_u32(sRing), aX = smem_u32(sX), aDY = smem_u32(sDY), aW = smem_u32(sW);
+  auto slot = [&](int parity, int j) { return (uint32_t)(parity ? R - 1 - j : j) * BUF; };  // byte offset into the ring
+  uint32_t ph_a = 0, ph_b = 0;
   const float wh = n.wh, w0 = n.w0;
   const long long s_begin = (long long)slice * n.slice_len;
   const long long s_end = min((long long)n.batch, s_begin + n.slice_len);
+  const int n_tiles = (int)((s_end - s_begin + kTile - 1) / kTile);
   float loss_acc = 0.f;
-  int it = 0;
 
-  // the sampler gather for one tile (column group 0): index -> coordinates, normalised target, weight
+  // ---- the sampler gather for one tile (column group 0): index -> coordinates, normalised target, weight
   float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f, gy = 0.f, gw = 0.f;
-  auto gather = [&](long long tile0) {
-    const long long s = tile0 + r;
+  auto gather = [&](int tile) {
+    const long long s = s_begin + (long long)tile * kTile + r;
     gx0 = gx1 = gx2 = gy = gw = 0.f;
-    if (tile0 < s_end && s < s_end) {
+    if (tile < n_tiles && s < s_end) {
       long long idx;
       if (n.mode == 0) idx = s;
       else if (a.idx) idx = a.idx[n.idx_off + s];
@@ -430,156 +451,229 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
       gw = brief_weight(n, idx, raw);
     }
   };
-  if (cg == 0) gather(s_begin);
-  mbar_wait(&bar_w, 0);
+  // epilogue warp -> MMA warp: this warp's operand rows are written (and its TMEM reads are done)
+  auto signal = [&](uint64_t* bar) {
+    tc_fence_before();
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  };
+  auto epi_sync = [&]() { named_bar_sync(1, NT); };  // epilogue threads only
 
-  for (long long tile0 = s_begin; tile0 < s_end; tile0 += kTile, ++it) {
-    TT(ctile);
-    const bool valid = tile0 + r < s_end;
-    const float yv = gy, wv = gw;
+  // ---- forward prologue of a tile: coordinates -> s_row / sX, layer 0 on CUDA cores -> a_0
+  float4 xf = make_float4(0.f, 0.f, 0.f, 0.f);  // coordinates of the forward tile's row, xb: of the backward tile's
+  float4 xb = xf;
+  auto fwd_prologue = [&](int parity) {
     if (cg == 0) {
       s_row[r] = make_float4(gx0, gx1, gx2, 0.f);
       // B operand of the dW0 contraction: [x_hi(3), 1, x_lo(3), 0]  (hi/lo split keeps fp32-grade coordinates)
       const float h0 = __half2float(__float2half_rn(gx0)), h1 = __half2float(__float2half_rn(gx1)),
                   h2 = __half2float(__float2half_rn(gx2));
-      *reinterpret_cast<uint4*>(sX + chunk_off(r, 0, kTile)) =
+      *reinterpret_cast<uint4*>(sX + parity * BLK + chunk_off(r, 0, kTile)) =
           make_uint4(pack_f16x2(h0, h1), pack_f16x2(h2, 1.0f), pack_f16x2(gx0 - h0, gx1 - h1), pack_f16x2(gx2 - h2, 0.f));
     }
-    __syncthreads();
-    const float4 xr = s_row[r];
-    // ---- forward, layer 0 (CUDA cores): features 16cg .. 16cg+15
+    epi_sync();
+    xf = s_row[r];
+    unsigned char* a0 = sRing + slot(parity, 0);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float z[8];
-      *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * cg + h, kTile)) =
-          first_layer8<false>(s_w0b, 16 * cg + 8 * h, xr.x, xr.y, xr.z, w0, z);
+      *reinterpret_cast<uint4*>(a0 + chunk_off(r, 2 * cg + h, kTile)) =
+          first_layer8<false>(s_w0b, 16 * cg + 8 * h, xf.x, xf.y, xf.z, w0, z);
     }
-    // ---- forward, hidden layers (tensor core); a_l -> sAct[l]
-    float th[16];
-    float ypart = 0.f;
-    for (int l = 1; l <= NH; ++l) {
-      TT(c0);
-      tc_fence_before();
-      fence_async_smem();
-      TT(c1);
-      __syncthreads();
-      TT(c2);
-      if (warp == 0 && elect_one()) {
-        tc_fence_after();
-        issue_forward<F>(TZ, aAct + (uint32_t)(l - 1) * BUF, aW + (uint32_t)(l - 1) * F * F * 2);
-        commit(&bar_mma);
-      }
-      TT(c3);
-      mbar_wait(&bar_mma, phase);
-      TT(c4);
-      phase ^= 1;
-      tc_fence_after();
-      float v[16];
-      tmem_ld16(my_tmem, v);
-      tmem_ld_wait();
-      TT(c5);
-      TACC(0, c1 - c0); TACC(1, c2 - c1); TACC(2, c3 - c2); TACC(3, c4 - c3); TACC(4, c5 - c4);
-      theta16(v, s_wb + (l - 1) * F + 16 * cg, wh, th);
+  };
+  // ---- forward stage j of a tile: z_j (in Zf) -> a_j ; at j == NH also the last layer's partial dot product
+  float th[16];      // sine arguments of the last hidden layer of the forward tile (dz_NH needs their cosines)
+  float ypart = 0.f;
+  auto issue_fwd = [&](int parity, int j) {  // elected thread
+    issue_forward<F>(TZF, aRing + slot(parity, j - 1), aW + (uint32_t)(j - 1) * F * F * 2);
+    commit(&bar_b);
+  };
+  auto fwd_epilogue = [&](int parity, int j) {
+    float v[16];
+    tmem_ld16(my_tmem, v);
+    tmem_ld_wait();
+    theta16(v, s_wb + (j - 1) * F + 16 * cg, wh, th);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
-      store_chunk16(sAct + (size_t)l * BUF, r, cg, v);
-      { TT(c6); TACC(5, c6 - c5); }
-      if (l == NH) {
+    for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
+    store_chunk16(sRing + slot(parity, j), r, cg, v);
+    if (j == NH) {
+      ypart = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
-          ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
-          ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
-        }
+      for (int i = 0; i < 16; i += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
+        ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
+        ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
       }
     }
-    // ---- loss (datal2, main.py:176-182) and the scaled output gradient
+  };
+  // ---- loss (datal2, main.py:176-182), scaled output gradient and dz_NH for the tile that just finished forward
+  auto loss_phase = [&](int tile) {
     s_y[cg][r] = ypart;
-    __syncthreads();
+    epi_sync();
     if (cg == 0) {
       float y = s_bl[0];
 #pragma unroll
       for (int c = 0; c < CW; ++c) y += s_y[c][r];
       float dys = 0.f;
-      if (valid) {
-        const float e = y - yv;
-        const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : wv;
+      if (s_begin + (long long)tile * kTile + r < s_end) {
+        const float e = y - gy;
+        const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : gw;
         loss_acc = fmaf(wt * e, e, loss_acc);
         dys = kGradScale * wt * e;
       }
       s_dy[r] = dys;
       *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
-      gather(tile0 + kTile);  // prefetch the next tile's samples; consumed at the top of the next iteration
+      gather(tile + 1);  // prefetch the next forward tile's samples (global loads complete under the next stages)
     }
-    __syncthreads();
-    {  // dz_NH = dy * Wlast * w * cos(w z_NH) from the sine arguments still in registers
-      const float dys = s_dy[r];
-      float dz[16];
+    epi_sync();
+    const float dys = s_dy[r];
+    float dz[16];
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
-        dz[i] = dys * w4.x * wh * fast_cos(th[i]); dz[i + 1] = dys * w4.y * wh * fast_cos(th[i + 1]);
-        dz[i + 2] = dys * w4.z * wh * fast_cos(th[i + 2]); dz[i + 3] = dys * w4.w * wh * fast_cos(th[i + 3]);
-      }
-      store_chunk16_sat(sDz, r, cg, dz);
+    for (int i = 0; i < 16; i += 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
+      dz[i] = dys * w4.x * wh * fast_cos(th[i]); dz[i + 1] = dys * w4.y * wh * fast_cos(th[i + 1]);
+      dz[i + 2] = dys * w4.z * wh * fast_cos(th[i + 2]); dz[i + 3] = dys * w4.w * wh * fast_cos(th[i + 3]);
     }
-    // ---- backward through the hidden layers
-    int cur = 0;
-    for (int l = NH; l >= 1; --l) {
-      tc_fence_before();
-      fence_async_smem();
-      __syncthreads();
-      if (warp == 0 && elect_one()) {
+    store_chunk16_sat(sDz, r, cg, dz);
+  };
+  // ---- backward stage l of a tile.  issue: what the epilogue waits for (z_{l-1} recomputed, dX_{l-1}) is committed
+  //      first; dW_l, db_l (+ dWlast at l == NH) follow and are tracked by the tile's next commit.
+  int cur = 0;
+  auto issue_bwd = [&](int parity, int l, bool accumulate) {  // elected thread
+    const uint32_t dzb = aDz + (uint32_t)cur * BUF;
+    if (l >= 2) issue_forward<F>(TZB, aRing + slot(parity, l - 2), aW + (uint32_t)(l - 2) * F * F * 2);
+    issue_dx<F>(TXB, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
+    commit(&bar_a);
+    issue_dw<F>(acc_addr(l - 1), dzb, aRing + slot(parity, l - 1), accumulate);
+    if (l == NH) issue_dw<16>(acc_addr(NH + 1), aRing + slot(parity, NH), aDY, accumulate);
+  };
+  auto bwd_epilogue = [&](int l) {  // dz_{l-1} = dX_{l-1} * w * cos(w z_{l-1})
+    float vx[16], dz[16];
+    if (l >= 2) {
+      float vz[16];
+      tmem_ld16(my_tmem + F, vz);
+      tmem_ld16(my_tmem + 2 * F, vx);
+      tmem_ld_wait();
+      theta16(vz, s_wb + (l - 2) * F + 16 * cg, wh, dz);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dz[i] = vx[i] * wh * fast_cos(dz[i]);
+    } else {  // layer 0: z_0 recomputed on CUDA cores from the backward tile's coordinates
+      tmem_ld16(my_tmem + 2 * F, vx);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 w = s_w0b[16 * cg + i];
+        float z = w.w;
+        z = fmaf(w.x, xb.x, z); z = fmaf(w.y, xb.y, z); z = fmaf(w.z, xb.z, z);
+        dz[i] = vx[i] * w0 * fast_cos(w0 * z);
+      }
+    }
+    store_chunk16_sat(sDz + (size_t)(cur ^ 1) * BUF, r, cg, dz);
+    cur ^= 1;
+  };
+
+  // ================================================ schedule ====================================================
+  mbar_wait(&bar_w, 0);
+  if (mma_warp) {
+    // ---- the MMA warp mirrors the epilogue warps' schedule; one elected lane issues
+    uint32_t ph_ra = 0, ph_rb = 0;
+    if (n_tiles > 0) {
+      for (int j = 1; j <= NH; ++j) {
+        mbar_wait(&bar_rb, ph_rb);
+        ph_rb ^= 1;
         tc_fence_after();
-        const uint32_t dzb = aDz + (uint32_t)cur * BUF;
-        // what the epilogue waits for: z_{l-1} (recomputed) and dX_{l-1}
-        if (l >= 2) issue_forward<F>(TZ, aAct + (uint32_t)(l - 2) * BUF, aW + (uint32_t)(l - 2) * F * F * 2);
-        issue_dx<F>(TX, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
-        commit(&bar_mma);
-        // off the critical path (tracked by the next commit): dW_l, db_l (+ dWlast, dblast)
-        issue_dw<F>(TDW + (uint32_t)(l - 1) * F, dzb, aAct + (uint32_t)(l - 1) * BUF, it > 0);
-        if (l == NH) issue_dw<16>(TDWL, aAct + (uint32_t)NH * BUF, aDY, it > 0);
+        if (elect_one()) issue_fwd(0, j);
+        __syncwarp();
       }
-      mbar_wait(&bar_mma, phase);
-      phase ^= 1;
+    }
+    for (int i = 0; i < n_tiles; ++i) {
+      const int pa = i & 1, pb = pa ^ 1;
+      const bool has_b = i + 1 < n_tiles;
+      mbar_wait(&bar_ra, ph_ra);  // dz_NH / sDY of tile i and a_0 / sX of tile i+1 are in place
+      ph_ra ^= 1;
       tc_fence_after();
-      float vx[16], dz[16];
-      if (l >= 2) {
-        float vz[16];
-        tmem_ld16(my_tmem, vz);
-        tmem_ld16(my_tmem + F, vx);
-        tmem_ld_wait();
-        theta16(vz, s_wb + (l - 2) * F + 16 * cg, wh, dz);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) dz[i] = vx[i] * wh * fast_cos(dz[i]);
-      } else {  // l == 1: dz_0 = dX_0 * w0 * cos(w0 z_0), z_0 recomputed on CUDA cores
-        tmem_ld16(my_tmem + F, vx);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float4 w = s_w0b[16 * cg + i];
-          float z = w.w;
-          z = fmaf(w.x, xr.x, z); z = fmaf(w.y, xr.y, z); z = fmaf(w.z, xr.z, z);
-          dz[i] = vx[i] * w0 * fast_cos(w0 * z);
+      if (elect_one()) {
+        issue_bwd(pa, NH, i > 0);
+        if (has_b) issue_fwd(pb, 1);
+      }
+      __syncwarp();
+      for (int j = 1; j <= NH; ++j) {
+        const int l = NH + 1 - j;
+        mbar_wait(&bar_ra, ph_ra);  // dz_{l-1} written
+        ph_ra ^= 1;
+        tc_fence_after();
+        cur ^= 1;  // mirrors bwd_epilogue's buffer flip
+        if (elect_one()) {
+          if (l > 1) {
+            issue_bwd(pa, l - 1, i > 0);
+          } else {  // dW0 += dz_0^T [x_hi, 1, x_lo]; its commit also covers dW_1, so waiting on it frees the tile
+            issue_dw<16>(acc_addr(NH), aDz + (uint32_t)cur * BUF, aX + pa * BLK, i > 0);
+            commit(&bar_a);
+          }
+        }
+        __syncwarp();
+        if (has_b && j < NH) {
+          mbar_wait(&bar_rb, ph_rb);  // a_j written
+          ph_rb ^= 1;
+          tc_fence_after();
+          if (elect_one()) issue_fwd(pb, j + 1);
+          __syncwarp();
         }
       }
-      store_chunk16_sat(sDz + (size_t)(cur ^ 1) * BUF, r, cg, dz);
-      cur ^= 1;
+      cur = 0;
     }
-    // ---- dW0 += dz_0^T [x_hi, 1, x_lo]; wait so that the next tile may overwrite sX / sDz / sAct
-    tc_fence_before();
-    fence_async_smem();
-    __syncthreads();
-    if (warp == 0 && elect_one()) {
+  } else {
+    // ---- epilogue warps
+    if (cg == 0) gather(0);
+    if (n_tiles > 0) {
+      // tile 0 walks forward alone
+      fwd_prologue(0);
+      signal(&bar_rb);
+      for (int j = 1; j <= NH; ++j) {
+        mbar_wait(&bar_b, ph_b);
+        ph_b ^= 1;
+        tc_fence_after();
+        fwd_epilogue(0, j);
+        if (j < NH) signal(&bar_rb);
+      }
+      loss_phase(0);
+      xb = xf;
+      cur = 0;
+    }
+    for (int i = 0; i < n_tiles; ++i) {  // tile i walks backward, tile i+1 forward (ring parity pb)
+      const int pb = (i & 1) ^ 1;
+      const bool has_b = i + 1 < n_tiles;
+      if (has_b) fwd_prologue(pb);
+      signal(&bar_ra);
+      for (int j = 1; j <= NH; ++j) {
+        const int l = NH + 1 - j;
+        // -- backward tile
+        mbar_wait(&bar_a, ph_a);
+        ph_a ^= 1;
+        tc_fence_after();
+        bwd_epilogue(l);
+        signal(&bar_ra);
+        // -- forward tile
+        if (has_b) {
+          mbar_wait(&bar_b, ph_b);
+          ph_b ^= 1;
+          tc_fence_after();
+          fwd_epilogue(pb, j);
+          if (j < NH) signal(&bar_rb);
+        }
+      }
+      mbar_wait(&bar_a, ph_a);  // tile i is done: its ring slots, sX and sDz may be reused
+      ph_a ^= 1;
       tc_fence_after();
-      issue_dw<16>(TDW0, aDz + (uint32_t)cur * BUF, aX, it > 0);
-      commit(&bar_mma);
+      if (has_b) {
+        loss_phase(i + 1);
+        xb = xf;
+        cur = 0;
+      }
     }
-    mbar_wait(&bar_mma, phase);
-    phase ^= 1;
-    tc_fence_after();
-    { TT(cend); TACC(6, cend - ctile); TACC(7, 1); }
   }
+  __syncthreads();
 
   // ---- slice epilogue: loss partial + gradient partials (TMEM -> global), scale removed in fp32
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
@@ -589,41 +683,42 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::FIT_MIN_BLOCKS) t
     if (lane == 0) s_red[q] = loss_acc;
   }
   float* part = a.partials + n.part_off + (long long)slice * n.P_dev;
-  for (int i = t; i < n.P_dev; i += TcCfg<F>::THREADS) part[i] = 0.f;
+  for (int i = t; i < n.P_dev; i += TcCfg<F>::FIT_THREADS) part[i] = 0.f;
   __syncthreads();
   if (t == 0) a.loss_partials[n.slice_off + slice] = (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]) * inv_count;
-  if (it > 0) {
+  if (n_tiles > 0 && !mma_warp) {
     const float unscale = 2.0f * inv_count / kGradScale;
-    const int o = q * 16 + lane;  // accumulator row held by this thread (M = 64 layout: lanes 0..15 of each quadrant)
-    const bool row_ok = lane < 16 && o < F;
+    // lanes 0..15 of a quadrant hold the even accumulator of a block, lanes 16..31 the odd one; row = 16q + lane%16
+    const int o = q * 16 + (lane & 15), half = lane >> 4;
     const int F4 = n.F4;
+    const int n_blocks = fit_acc_blocks(NH);
     float v[16];
-    for (int l = 1; l <= NH; ++l) {
-      tmem_ld16(my_tmem + 2 * F + (l - 1) * F, v);
+    for (int b = 0; b < n_blocks; ++b) {
+      const int i = 2 * b + half;  // accumulator index served by this thread in block b
+      tmem_ld16(my_tmem + 3 * F + b * F, v);
       tmem_ld_wait();
-      if (row_ok && o < f) {
+      if (i < NH) {  // dW_{i+1}, db_{i+1}
+        if (o < f) {
+          const int l = i + 1;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int k = 16 * cg + i;
-          if (k < f) part[dl_W(n, l) + o * F4 + k] = v[i] * unscale;
-          else if (k == f) part[dl_b(n, l) + o] = v[i] * unscale;
+          for (int c = 0; c < 16; ++c) {
+            const int k = 16 * cg + c;
+            if (k < f) part[dl_W(n, l) + o * F4 + k] = v[c] * unscale;
+            else if (k == f) part[dl_b(n, l) + o] = v[c] * unscale;
+          }
         }
-      }
-    }
-    if (cg == 0) {
-      tmem_ld16(my_tmem + 2 * F + NH * F, v);  // dW0 block
-      tmem_ld_wait();
-      if (row_ok && o < f) {
-        part[dl_W0(n) + 4 * o + 0] = (v[0] + v[4]) * unscale;
-        part[dl_W0(n) + 4 * o + 1] = (v[1] + v[5]) * unscale;
-        if (n.in_dim == 3) part[dl_W0(n) + 4 * o + 2] = (v[2] + v[6]) * unscale;
-        part[dl_b0(n) + o] = v[3] * unscale;
-      }
-      tmem_ld16(my_tmem + 2 * F + NH * F + 16, v);  // dWlast block: row = feature of a_NH, column 0
-      tmem_ld_wait();
-      if (row_ok) {
-        if (o < f) part[dl_Wlast(n) + o] = v[0] * unscale;
-        else if (o == f) part[dl_blast(n)] = v[0] * unscale;
+      } else if (i == NH) {  // dW0 block
+        if (cg == 0 && o < f) {
+          part[dl_W0(n) + 4 * o + 0] = (v[0] + v[4]) * unscale;
+          part[dl_W0(n) + 4 * o + 1] = (v[1] + v[5]) * unscale;
+          if (n.in_dim == 3) part[dl_W0(n) + 4 * o + 2] = (v[2] + v[6]) * unscale;
+          part[dl_b0(n) + o] = v[3] * unscale;
+        }
+      } else if (i == NH + 1) {  // dWlast block: row = feature of a_NH, column 0; row f is dblast
+        if (cg == 0) {
+          if (o < f) part[dl_Wlast(n) + o] = v[0] * unscale;
+          else if (o == f) part[dl_blast(n)] = v[0] * unscale;
+        }
       }
     }
   }
@@ -639,16 +734,16 @@ int tc_fpad(int f) { return ((f + 1 + 15) / 16) * 16; }
 int tc_fit_ctas_per_sm(int F) { return F >= 48 ? 1 : 2; }  // == TcCfg<F>::FIT_MIN_BLOCKS
 size_t tc_wpack_bytes(int F, int L) { return img_bytes(F, L - 2); }
 size_t tc_eval_smem(int F, int L) { return img_bytes_padded(F, L - 2) + (size_t)kTile * F * 2; }
-size_t tc_fit_smem(int F, int L) {
-  return (size_t)(2 + (L - 1)) * kTile * F * 2 + 2 * (size_t)kTile * 16 * 2 + img_bytes_padded(F, L - 2);
+size_t tc_fit_smem(int F, int L) {  // sDz[2] + ring[NS + 2] + sX[2] + sDY + image
+  return (size_t)(2 + (L - 1) + 2) * kTile * F * 2 + 3 * (size_t)kTile * 16 * 2 + img_bytes_padded(F, L - 2);
 }
 
 bool tc_supported(int f, int L, int in_dim, int out_dim) {
   const int F = tc_fpad(f);
   if (out_dim != 1 || (in_dim != 2 && in_dim != 3)) return false;
   if (L < 3 || F > 64) return false;
-  if ((L - 2) * F + 2 * F + 32 > 512) return false;  // TMEM: Z, X, dW_l accumulators, dW0 / dWlast blocks
-  if (tc_fit_smem(F, L) > 225 * 1024) return false;
+  if (3 * F + fit_acc_blocks(L - 2) * F > 512) return false;  // TMEM: Zf, Zb, Xb + packed dW accumulators
+  if (tc_fit_smem(F, L) > 221 * 1024) return false;           // + ~5 KB static shared memory <= 227 KB
   return true;
 }
 
@@ -684,7 +779,7 @@ static cudaError_t launch_fit_f(const FitArgs& a, int L_max, int n_blocks, cudaS
   const size_t smem = tc_fit_smem(F, L_max) < 49152 ? 49152 : tc_fit_smem(F, L_max);
   cudaError_t e = cudaFuncSetAttribute(tc_fit_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fit_kernel<F><<<n_blocks, TcCfg<F>::THREADS, smem, st>>>(a);
+  tc_fit_kernel<F><<<n_blocks, TcCfg<F>::FIT_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -700,10 +795,3 @@ cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int L_max, int n_blocks, 
 
 }  // namespace brief
 
-#ifdef BRIEF_TC_TIMING
-extern "C" int brief_debug_read_timing(unsigned long long* out, int reset) {
-  cudaMemcpyFromSymbol(out, brief::g_tc_timing, sizeof(unsigned long long) * 16);
-  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(brief::g_tc_timing, z, sizeof z); }
-  return 0;
-}
-#endif

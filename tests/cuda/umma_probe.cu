@@ -52,6 +52,11 @@ __global__ void __launch_bounds__(128) probe(const float* A_in, const float* G_i
     for (int k = 0; k < 128 / 16; ++k)
       mma_f16(tm + 3 * F, make_desc(aG + k * 2 * 128, 128, 2048), make_desc(aA + k * 2 * 128, 128, 2048),
                make_idesc(64, F, true, true, true), k > 0);
+    // 5) a second M = 64 accumulator in the SAME columns as 4), 16 lanes higher (the unused half of every quadrant):
+    //    D5[o][k] = sum_s A[s][o] G[s][k]  (operands swapped so that the result differs from 4)
+    for (int k = 0; k < 128 / 16; ++k)
+      mma_f16(tm + 3 * F + (16u << 16), make_desc(aA + k * 2 * 128, 128, 2048), make_desc(aG + k * 2 * 128, 128, 2048),
+               make_idesc(64, F, true, true, true), k > 0);
     commit(&bar);
   }
   mbar_wait(&bar, 0);
@@ -122,6 +127,16 @@ int run() {
     printf(" %d", found);
   }
   printf("\n");
+  {  // 5) rows of the swapped product must sit at lane 32*(o/16) + 16 + o%16, and 4) must be intact
+    int bad5 = 0, bad4 = 0;
+    for (int o = 0; o < F && o < 64; ++o)
+      for (int k = 0; k < F; ++k) {
+        float r5 = 0; for (int s2 = 0; s2 < 128; ++s2) r5 += A[s2 * F + o] * G[s2 * F + k];
+        bad5 += d4[(32 * (o / 16) + 16 + o % 16) * F + k] != r5;
+        bad4 += d4[(32 * (o / 16) + o % 16) * F + k] != ref3[o * F + k];
+      }
+    printf("F=%d lane-offset-16 accumulator: mismatches %d (lower half intact: %d mismatches)\n", F, bad5, bad4);
+  }
   printf("F=%d forward mismatches %d, dX mismatches %d, dW mismatches %d  (d1[0..3]= %g %g %g %g)\n", F, bad1, bad2, bad3,
          d1[0], d1[1], d1[2], d1[3]);
   return bad1 + bad2 + bad3;
