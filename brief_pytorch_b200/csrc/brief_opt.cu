@@ -88,7 +88,7 @@ cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st) {
 
 // ---- fp16 operand image for the tcgen05 kernels ----------------------------------------------------
 // Image of network n (bytes, at wpack + n.wpack_off), F = F_PAD, NH = L-2:
-//   [NH] hidden weights, fp16, UMMA no-swizzle core-matrix layout: element (o,k) of layer l at
+//   [NH] hidden weights TIMES w_hidden, fp16, UMMA no-swizzle core-matrix layout: element (o,k) of layer l at
 //        l*F*F*2 + ((k/8)*(F/8) + o/8)*128 + (o%8)*16 + (k%8)*2       (8x8 cores, K contiguous)
 //   then fp32: first layer float4 (wx,wy,wz,b0) x F | omega*bias [NH][F] | Wlast [F] | blast,0,0,0
 // Pad column f (the first unused feature) is the constant-one feature of the fit kernel: its weights are zero
@@ -107,7 +107,9 @@ __global__ void pack_kernel(const NetDev* nets, int n_nets, const float* __restr
     if (i < n_hidden) {
       const int l = i / (F * F), r = i - l * F * F;
       const int o = r / F, k = r - o * F;
-      const float w = (o < f && k < f) ? P[dl_W(n, l + 1) + o * F4 + k] : 0.f;
+      // hidden weights are stored pre-multiplied by the hidden omega: the MMA then yields w*z directly, and the dX
+      // contraction yields w * dz W, which is the factor the chain rule needs (one FMUL less per element)
+      const float w = (o < f && k < f) ? __fmul_rn(n.wh, P[dl_W(n, l + 1) + o * F4 + k]) : 0.f;
       const size_t off = (size_t)l * F * F * 2 + ((size_t)(k >> 3) * (F >> 3) + (o >> 3)) * 128 + (o & 7) * 16 + (k & 7) * 2;
       *reinterpret_cast<__half*>(img + off) = __float2half_rn(w);
     } else {

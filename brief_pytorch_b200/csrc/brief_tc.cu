@@ -49,7 +49,7 @@ constexpr uint32_t kActLBO = (kTile / 8) * 128;  // 2048: feature-group stride o
 __host__ __device__ constexpr int tmem_cols_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 // ---- packed image (written by pack_kernel, brief_opt.cu) ------------------------------------------------------
-//   [NH][F*F] fp16 hidden weights (interleaved, R = F)  |  fp32 side block:
+//   [NH][F*F] fp16 hidden weights times w_hidden (interleaved, R = F)  |  fp32 side block:
 //   float4 (W0x, W0y, W0z, b0) x F | w_hidden * b_l [NH][F] | Wlast [F] | blast, 0, 0, 0
 __host__ __device__ constexpr size_t img_hidden_bytes(int F, int NH) { return (size_t)NH * F * F * 2; }
 __host__ __device__ constexpr size_t img_side_floats(int F, int NH) { return (size_t)4 * F + (size_t)NH * F + F + 4; }
@@ -130,7 +130,7 @@ template <int F>
 struct TcCfg {
   static constexpr int CW = F / 16;
   static constexpr int THREADS = 128 * CW;                                // epilogue threads
-  static constexpr int FIT_THREADS = THREADS + 32;                        // + one warp that only issues MMAs
+  static constexpr int FIT_THREADS = THREADS + 64;                        // + MMA-issue warp + sampler warp
   static constexpr int EVAL_MIN_BLOCKS = F >= 48 ? 2 : F == 32 ? 4 : 8;  // ~1024 threads per SM
   static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : 2;                  // must match fit_ctas_per_sm()
 };
@@ -150,13 +150,13 @@ __device__ __forceinline__ void store_chunk16_sat(unsigned char* buf, int r, int
                  pack_f16x2_sat(v[14], v[15]));
 }
 
-// theta_i = w * z_i + (w * b)_i for the thread's 16 columns
-__device__ __forceinline__ void theta16(const float* z, const float* __restrict__ wb, float w, float* th) {
+// theta_i = (w z)_i + (w b)_i for the thread's 16 columns (the packed weights already carry the hidden omega)
+__device__ __forceinline__ void theta16(const float* wz, const float* __restrict__ wb, float* th) {
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
     const float4 b4 = *reinterpret_cast<const float4*>(wb + i);
-    th[i] = fmaf(z[i], w, b4.x); th[i + 1] = fmaf(z[i + 1], w, b4.y);
-    th[i + 2] = fmaf(z[i + 2], w, b4.z); th[i + 3] = fmaf(z[i + 3], w, b4.w);
+    th[i] = wz[i] + b4.x; th[i + 1] = wz[i + 1] + b4.y;
+    th[i + 2] = wz[i + 2] + b4.z; th[i + 3] = wz[i + 3] + b4.w;
   }
 }
 
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) 
       float v[16], th[16];
       tmem_ld16(my_tmem, v);
       tmem_ld_wait();
-      theta16(v, s_wb + (l - 1) * F + 16 * cg, wh, th);
+      theta16(v, s_wb + (l - 1) * F + 16 * cg, th);
       if (DUMP && valid) {
         float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
         for (int i = 0; i < 16; ++i)
@@ -365,20 +365,21 @@ __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) { return tmem_col
 template <int F>
 __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
   constexpr int CW = TcCfg<F>::CW;
-  constexpr int NT = TcCfg<F>::THREADS;   // epilogue threads; warp NT/32 is the MMA warp
+  constexpr int NT = TcCfg<F>::THREADS;   // epilogue threads; warp NW is the MMA warp, warp NW+1 the sampler warp
   constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb;
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_gfull[2], bar_gfree[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float4 s_row[kTile];
+  __shared__ __align__(16) float4 s_g[2][kTile];  // sampler staging: (x0, x1, x2, normalised target) per row
+  __shared__ float s_gw[2][kTile];                //                  loss weight per row
   __shared__ float s_y[CW][kTile];
   __shared__ float s_dy[kTile];
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool mma_warp = warp == NW;
-  const int q = warp & 3, cg = mma_warp ? CW : (warp >> 2), r = 32 * q + lane;
+  const bool mma_warp = warp == NW, sampler_warp = warp == NW + 1;
+  const int q = warp & 3, cg = warp >= NW ? CW : (warp >> 2), r = 32 * q + lane;
   const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
   const int net_id = a.work_net[wi];
   const int slice = blockIdx.x - a.work_prefix[wi];
@@ -389,6 +390,10 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
     mbar_init(&bar_b, 1);
     mbar_init(&bar_ra, NW);  // "operands of the backward tile are in place": one arrival per epilogue warp
     mbar_init(&bar_rb, NW);  // same for the forward tile
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&bar_gfull[k], 1);    // sampler warp: staging slot k holds a tile's samples
+      mbar_init(&bar_gfree[k], NW);   // epilogue warps: staging slot k has been consumed
+    }
     fence_mbar_init();
   }
   __syncthreads();
@@ -435,20 +440,26 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   const int n_tiles = (int)((s_end - s_begin + kTile - 1) / kTile);
   float loss_acc = 0.f;
 
-  // ---- the sampler gather for one tile (column group 0): index -> coordinates, normalised target, weight
-  float gx0 = 0.f, gx1 = 0.f, gx2 = 0.f, gy = 0.f, gw = 0.f;
-  auto gather = [&](int tile) {
-    const long long s = s_begin + (long long)tile * kTile + r;
-    gx0 = gx1 = gx2 = gy = gw = 0.f;
-    if (tile < n_tiles && s < s_end) {
-      long long idx;
-      if (n.mode == 0) idx = s;
-      else if (a.idx) idx = a.idx[n.idx_off + s];
-      else idx = brief_sample_index(a.seed, a.step, (uint32_t)net_id, (uint64_t)s, (uint64_t)n.n_vox);
-      brief_coords(n, a.axes, idx, gx0, gx1, gx2);
-      const float raw = brief_raw_value(n, idx);
-      gy = brief_normalize(n, raw);
-      gw = brief_weight(n, idx, raw);
+  // ---- the sampler (main.py:126-163 / whole-block cube) for one tile, run by the sampler warp one tile ahead of its
+  //      use: index -> coordinates (axis tables), raw voxel -> normalised target, loss weight; 4 rows per lane
+  auto sample_tile = [&](int tile, int slot_id) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int row = lane + 32 * h;
+      const long long s = s_begin + (long long)tile * kTile + row;
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f, yv = 0.f, wv = 0.f;
+      if (s < s_end) {
+        long long idx;
+        if (n.mode == 0) idx = s;
+        else if (a.idx) idx = a.idx[n.idx_off + s];
+        else idx = brief_sample_index(a.seed, a.step, (uint32_t)net_id, (uint64_t)s, (uint64_t)n.n_vox);
+        brief_coords(n, a.axes, idx, x0, x1, x2);
+        const float raw = brief_raw_value(n, idx);
+        yv = brief_normalize(n, raw);
+        wv = brief_weight(n, idx, raw);
+      }
+      s_g[slot_id][row] = make_float4(x0, x1, x2, yv);
+      s_gw[slot_id][row] = wv;
     }
   };
   // epilogue warp -> MMA warp: this warp's operand rows are written (and its TMEM reads are done)
@@ -463,17 +474,17 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   // ---- forward prologue of a tile: coordinates -> s_row / sX, layer 0 on CUDA cores -> a_0
   float4 xf = make_float4(0.f, 0.f, 0.f, 0.f);  // coordinates of the forward tile's row, xb: of the backward tile's
   float4 xb = xf;
-  auto fwd_prologue = [&](int parity) {
+  auto fwd_prologue = [&](int tile) {
+    const int parity = tile & 1;
+    mbar_wait(&bar_gfull[parity], (uint32_t)(tile >> 1) & 1);
+    xf = s_g[parity][r];
     if (cg == 0) {
-      s_row[r] = make_float4(gx0, gx1, gx2, 0.f);
       // B operand of the dW0 contraction: [x_hi(3), 1, x_lo(3), 0]  (hi/lo split keeps fp32-grade coordinates)
-      const float h0 = __half2float(__float2half_rn(gx0)), h1 = __half2float(__float2half_rn(gx1)),
-                  h2 = __half2float(__float2half_rn(gx2));
+      const float h0 = __half2float(__float2half_rn(xf.x)), h1 = __half2float(__float2half_rn(xf.y)),
+                  h2 = __half2float(__float2half_rn(xf.z));
       *reinterpret_cast<uint4*>(sX + parity * BLK + chunk_off(r, 0, kTile)) =
-          make_uint4(pack_f16x2(h0, h1), pack_f16x2(h2, 1.0f), pack_f16x2(gx0 - h0, gx1 - h1), pack_f16x2(gx2 - h2, 0.f));
+          make_uint4(pack_f16x2(h0, h1), pack_f16x2(h2, 1.0f), pack_f16x2(xf.x - h0, xf.y - h1), pack_f16x2(xf.z - h2, 0.f));
     }
-    epi_sync();
-    xf = s_row[r];
     unsigned char* a0 = sRing + slot(parity, 0);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
     float v[16];
     tmem_ld16(my_tmem, v);
     tmem_ld_wait();
-    theta16(v, s_wb + (j - 1) * F + 16 * cg, wh, th);
+    theta16(v, s_wb + (j - 1) * F + 16 * cg, th);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
     store_chunk16(sRing + slot(parity, j), r, cg, v);
@@ -517,23 +528,24 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
       for (int c = 0; c < CW; ++c) y += s_y[c][r];
       float dys = 0.f;
       if (s_begin + (long long)tile * kTile + r < s_end) {
-        const float e = y - gy;
-        const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : gw;
+        const float e = y - xf.w;  // xf.w: the row's normalised target
+        const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : s_gw[tile & 1][r];
         loss_acc = fmaf(wt * e, e, loss_acc);
         dys = kGradScale * wt * e;
       }
       s_dy[r] = dys;
       *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
-      gather(tile + 1);  // prefetch the next forward tile's samples (global loads complete under the next stages)
     }
     epi_sync();
-    const float dys = s_dy[r];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_gfree[tile & 1]);  // staging slot consumed (coordinates live on in xf / xb)
+    const float dys = s_dy[r] * wh;
     float dz[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
       const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
-      dz[i] = dys * w4.x * wh * fast_cos(th[i]); dz[i + 1] = dys * w4.y * wh * fast_cos(th[i + 1]);
-      dz[i + 2] = dys * w4.z * wh * fast_cos(th[i + 2]); dz[i + 3] = dys * w4.w * wh * fast_cos(th[i + 3]);
+      dz[i] = dys * w4.x * fast_cos(th[i]); dz[i + 1] = dys * w4.y * fast_cos(th[i + 1]);
+      dz[i + 2] = dys * w4.z * fast_cos(th[i + 2]); dz[i + 3] = dys * w4.w * fast_cos(th[i + 3]);
     }
     store_chunk16_sat(sDz, r, cg, dz);
   };
@@ -555,10 +567,11 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
       tmem_ld16(my_tmem + F, vz);
       tmem_ld16(my_tmem + 2 * F, vx);
       tmem_ld_wait();
-      theta16(vz, s_wb + (l - 2) * F + 16 * cg, wh, dz);
+      theta16(vz, s_wb + (l - 2) * F + 16 * cg, dz);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dz[i] = vx[i] * wh * fast_cos(dz[i]);
+      for (int i = 0; i < 16; ++i) dz[i] = vx[i] * fast_cos(dz[i]);  // vx = w * (dz_l W_l): omega-scaled weights
     } else {  // layer 0: z_0 recomputed on CUDA cores from the backward tile's coordinates
+      const float w0_over_wh = w0 / wh;
       tmem_ld16(my_tmem + 2 * F, vx);
       tmem_ld_wait();
 #pragma unroll
@@ -566,7 +579,7 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
         const float4 w = s_w0b[16 * cg + i];
         float z = w.w;
         z = fmaf(w.x, xb.x, z); z = fmaf(w.y, xb.y, z); z = fmaf(w.z, xb.z, z);
-        dz[i] = vx[i] * w0 * fast_cos(w0 * z);
+        dz[i] = vx[i] * w0_over_wh * fast_cos(w0 * z);
       }
     }
     store_chunk16_sat(sDz + (size_t)(cur ^ 1) * BUF, r, cg, dz);
@@ -623,9 +636,16 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
       }
       cur = 0;
     }
+  } else if (sampler_warp) {
+    // ---- the sampler warp runs up to two tiles ahead of the epilogue warps
+    for (int k = 0; k < n_tiles; ++k) {
+      if (k >= 2) mbar_wait(&bar_gfree[k & 1], (uint32_t)((k >> 1) - 1) & 1);
+      sample_tile(k, k & 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_gfull[k & 1]);
+    }
   } else {
     // ---- epilogue warps
-    if (cg == 0) gather(0);
     if (n_tiles > 0) {
       // tile 0 walks forward alone
       fwd_prologue(0);
@@ -644,7 +664,7 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
     for (int i = 0; i < n_tiles; ++i) {  // tile i walks backward, tile i+1 forward (ring parity pb)
       const int pb = (i & 1) ^ 1;
       const bool has_b = i + 1 < n_tiles;
-      if (has_b) fwd_prologue(pb);
+      if (has_b) fwd_prologue(i + 1);
       signal(&bar_ra);
       for (int j = 1; j <= NH; ++j) {
         const int l = NH + 1 - j;
@@ -686,7 +706,7 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   for (int i = t; i < n.P_dev; i += TcCfg<F>::FIT_THREADS) part[i] = 0.f;
   __syncthreads();
   if (t == 0) a.loss_partials[n.slice_off + slice] = (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]) * inv_count;
-  if (n_tiles > 0 && !mma_warp) {
+  if (n_tiles > 0 && warp < NW) {
     const float unscale = 2.0f * inv_count / kGradScale;
     // lanes 0..15 of a quadrant hold the even accumulator of a block, lanes 16..31 the odd one; row = 16q + lane%16
     const int o = q * 16 + (lane & 15), half = lane >> 4;
