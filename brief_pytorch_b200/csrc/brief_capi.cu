@@ -248,7 +248,8 @@ int finalize(BriefGroup* g, cudaStream_t st) {
       tc_tiles[n.F_PAD / 16] += (b + kTcTile - 1) / kTcTile;
     }
   for (int b = 1; b < kBuckets; ++b) {
-    const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(16 * b);
+    if (tc_tiles[b] == 0) continue;
+    const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(16 * b, g->tc_L[b]);
     tc_tps[b] = std::max<long long>(1, (tc_tiles[b] + wave - 1) / wave);
   }
   long long slice_total = 0, part_total = 0, idx_total = 0;

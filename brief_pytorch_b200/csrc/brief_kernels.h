@@ -88,7 +88,7 @@ cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, uns
 // brief_tc.cu (tcgen05 path)
 bool tc_supported(int f, int L, int in_dim, int out_dim);
 int tc_fpad(int f);
-int tc_fit_ctas_per_sm(int F_PAD);
+int tc_fit_ctas_per_sm(int F_PAD, int L);
 size_t tc_wpack_bytes(int F_PAD, int L);
 size_t tc_eval_smem(int F_PAD, int L);
 size_t tc_fit_smem(int F_PAD, int L);

@@ -132,7 +132,7 @@ struct TcCfg {
   static constexpr int THREADS = 128 * CW;                                // epilogue threads
   static constexpr int FIT_THREADS = THREADS + 64;                        // + MMA-issue warp + sampler warp
   static constexpr int EVAL_MIN_BLOCKS = F >= 48 ? 2 : F == 32 ? 4 : 8;  // ~1024 threads per SM
-  static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : 2;                  // must match fit_ctas_per_sm()
+  static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 4;    // must match tc_fit_ctas_per_sm()
 };
 
 __device__ __forceinline__ void store_chunk16(unsigned char* buf, int r, int cg, const float* v) {
@@ -702,8 +702,10 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
     for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
     if (lane == 0) s_red[q] = loss_acc;
   }
-  float* part = a.partials + n.part_off + (long long)slice * n.P_dev;
-  for (int i = t; i < n.P_dev; i += TcCfg<F>::FIT_THREADS) part[i] = 0.f;
+  // The slot image (padded device layout, pads zero) is assembled in shared memory — the operand buffers are dead
+  // by now — and leaves with coalesced 16-byte stores; scattered 4-byte stores from the accumulator rows cost ~10 us.
+  float* img = reinterpret_cast<float*>(smem);
+  for (int i = t; i < n.P_dev; i += TcCfg<F>::FIT_THREADS) img[i] = 0.f;
   __syncthreads();
   if (t == 0) a.loss_partials[n.slice_off + slice] = (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]) * inv_count;
   if (n_tiles > 0 && warp < NW) {
@@ -723,24 +725,30 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const int k = 16 * cg + c;
-            if (k < f) part[dl_W(n, l) + o * F4 + k] = v[c] * unscale;
-            else if (k == f) part[dl_b(n, l) + o] = v[c] * unscale;
+            if (k < f) img[dl_W(n, l) + o * F4 + k] = v[c] * unscale;
+            else if (k == f) img[dl_b(n, l) + o] = v[c] * unscale;
           }
         }
       } else if (i == NH) {  // dW0 block
         if (cg == 0 && o < f) {
-          part[dl_W0(n) + 4 * o + 0] = (v[0] + v[4]) * unscale;
-          part[dl_W0(n) + 4 * o + 1] = (v[1] + v[5]) * unscale;
-          if (n.in_dim == 3) part[dl_W0(n) + 4 * o + 2] = (v[2] + v[6]) * unscale;
-          part[dl_b0(n) + o] = v[3] * unscale;
+          img[dl_W0(n) + 4 * o + 0] = (v[0] + v[4]) * unscale;
+          img[dl_W0(n) + 4 * o + 1] = (v[1] + v[5]) * unscale;
+          if (n.in_dim == 3) img[dl_W0(n) + 4 * o + 2] = (v[2] + v[6]) * unscale;
+          img[dl_b0(n) + o] = v[3] * unscale;
         }
       } else if (i == NH + 1) {  // dWlast block: row = feature of a_NH, column 0; row f is dblast
         if (cg == 0) {
-          if (o < f) part[dl_Wlast(n) + o] = v[0] * unscale;
-          else if (o == f) part[dl_blast(n)] = v[0] * unscale;
+          if (o < f) img[dl_Wlast(n) + o] = v[0] * unscale;
+          else if (o == f) img[dl_blast(n)] = v[0] * unscale;
         }
       }
     }
+  }
+  __syncthreads();
+  {
+    float4* dst = reinterpret_cast<float4*>(a.partials + n.part_off + (long long)slice * n.P_dev);
+    const float4* src = reinterpret_cast<const float4*>(img);
+    for (int i = t; i < (n.P_dev >> 2); i += TcCfg<F>::FIT_THREADS) dst[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -751,11 +759,22 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
 // host side
 // ==================================================================================================================
 int tc_fpad(int f) { return ((f + 1 + 15) / 16) * 16; }
-int tc_fit_ctas_per_sm(int F) { return F >= 48 ? 1 : 2; }  // == TcCfg<F>::FIT_MIN_BLOCKS
+
 size_t tc_wpack_bytes(int F, int L) { return img_bytes(F, L - 2); }
 size_t tc_eval_smem(int F, int L) { return img_bytes_padded(F, L - 2) + (size_t)kTile * F * 2; }
 size_t tc_fit_smem(int F, int L) {  // sDz[2] + ring[NS + 2] + sX[2] + sDY + image
   return (size_t)(2 + (L - 1) + 2) * kTile * F * 2 + 3 * (size_t)kTile * 16 * 2 + img_bytes_padded(F, L - 2);
+}
+
+// resident fit CTAs per SM: the launch bound (registers), shared memory (dynamic + ~8 KB static) and TMEM columns
+int tc_fit_ctas_per_sm(int F, int L) {
+  const int by_bound = F >= 48 ? 1 : F == 32 ? 2 : 4;  // == TcCfg<F>::FIT_MIN_BLOCKS
+  const size_t dyn = tc_fit_smem(F, L) < 49152 ? 49152 : tc_fit_smem(F, L);
+  const int by_smem = (int)((size_t)227 * 1024 / (dyn + 8192));
+  const int by_tmem = 512 / fit_tmem_cols(F, L - 2);
+  int r = by_bound < by_smem ? by_bound : by_smem;
+  r = r < by_tmem ? r : by_tmem;
+  return r < 1 ? 1 : r;
 }
 
 bool tc_supported(int f, int L, int in_dim, int out_dim) {
