@@ -130,6 +130,7 @@ template <int F>
 struct TcCfg {
   static constexpr int CW = F / 16;
   static constexpr int THREADS = 128 * CW;                                // epilogue threads
+  static constexpr int EVAL_THREADS = THREADS + 32;                       // + one warp that only issues MMAs
   static constexpr int FIT_THREADS = THREADS + 64;                        // + MMA-issue warp + sampler warp
   static constexpr int EVAL_MIN_BLOCKS = F >= 48 ? 2 : F == 32 ? 4 : 8;  // ~1024 threads per SM
   static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 4;    // must match tc_fit_ctas_per_sm()
@@ -164,18 +165,21 @@ __device__ __forceinline__ void theta16(const float* wz, const float* __restrict
 // forward / decompress
 // ==================================================================================================================
 template <int F, bool DUMP>
-__global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) tc_eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(TcCfg<F>::EVAL_THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) tc_eval_kernel(EvalArgs a) {
   constexpr int CW = TcCfg<F>::CW;
+  constexpr int NT = TcCfg<F>::THREADS;  // epilogue threads; warp NW only issues MMAs (see the fit kernel)
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_r;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float4 s_row[kTile];
   __shared__ float s_y[CW][kTile];
   __shared__ __align__(16) unsigned short s_out[kTile];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;
+  const bool mma_warp = warp == NW;
+  const int q = warp & 3, cg = mma_warp ? CW : (warp >> 2), r = 32 * q + lane;
   int net_id;
   long long chunk;
   if (a.single_net >= 0) {
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) 
   if (t == 0) {
     mbar_init(&bar_w, 1);
     mbar_init(&bar_mma, 1);
+    mbar_init(&bar_r, NW);  // "the operand rows of this layer are written": one arrival per epilogue warp
     fence_mbar_init();
   }
   constexpr int TCOLS = tmem_cols_pow2(F);
@@ -218,7 +223,6 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) 
   const long long n_tiles = (total + kTile - 1) / kTile;
   const long long tile_begin = chunk * kEvalTilesPerBlock;
   const long long tile_end = min(n_tiles, tile_begin + kEvalTilesPerBlock);
-  uint32_t phase = 0;
   const float wh = n.wh;
 
   auto load_row = [&](long long tile) {  // column group 0 fetches the tile's coordinates for everyone
@@ -235,98 +239,114 @@ __global__ void __launch_bounds__(TcCfg<F>::THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) 
     }
     s_row[r] = make_float4(x0, x1, x2, 0.f);
   };
+  auto signal = [&]() {  // epilogue warp -> MMA warp
+    tc_fence_before();
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_r);
+  };
   if (cg == 0) load_row(tile_begin);
   mbar_wait(&bar_w, 0);
   __syncthreads();
 
-  for (long long tile = tile_begin; tile < tile_end; ++tile) {
-    const long long s = tile * kTile + r;
-    const bool valid = s < total;
-    const float4 xr = s_row[r];
-    // ---- layer 0 on CUDA cores -> fp16 operand rows (this thread: features 16cg .. 16cg+15)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float z[8];
-      const uint4 pk = first_layer8<DUMP>(s_w0b, 16 * cg + 8 * h, xr.x, xr.y, xr.z, n.w0, z);
-      if (DUMP && valid)
-        for (int i = 0; i < 8; ++i)
-          if (16 * cg + 8 * h + i < n.f) a.layers_out[s * n.f + 16 * cg + 8 * h + i] = z[i];
-      *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * cg + h, kTile)) = pk;
-    }
-    float ypart = 0.f;
-    // ---- hidden layers on the tensor core
-    for (int l = 1; l <= NH; ++l) {
-      tc_fence_before();
-      fence_async_smem();
-      __syncthreads();
-      if (warp == 0 && elect_one()) {
+  if (mma_warp) {
+    uint32_t ph_r = 0;
+    for (long long tile = tile_begin; tile < tile_end; ++tile)
+      for (int l = 1; l <= NH; ++l) {
+        mbar_wait(&bar_r, ph_r);
+        ph_r ^= 1;
         tc_fence_after();
-        issue_forward<F>(tm, aAct, aW + (uint32_t)(l - 1) * F * F * 2);
-        commit(&bar_mma);
-      }
-      mbar_wait(&bar_mma, phase);
-      phase ^= 1;
-      tc_fence_after();
-      float v[16], th[16];
-      tmem_ld16(my_tmem, v);
-      tmem_ld_wait();
-      theta16(v, s_wb + (l - 1) * F + 16 * cg, th);
-      if (DUMP && valid) {
-        float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
-        for (int i = 0; i < 16; ++i)
-          if (16 * cg + i < n.f) zdump[16 * cg + i] = th[i] / wh;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
-      if (l < NH) {
-        store_chunk16(sAct, r, cg, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
-          ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
-          ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
+        if (elect_one()) {
+          issue_forward<F>(tm, aAct, aW + (uint32_t)(l - 1) * F * F * 2);
+          commit(&bar_mma);
         }
+        __syncwarp();
       }
-    }
-    // ---- last layer: fixed-order sum of the column groups' partial dot products, then the output epilogue
-    s_y[cg][r] = ypart;
-    __syncthreads();
-    const bool full = tile * kTile + kTile <= total;
-    if (cg == 0) {
-      float y = s_bl[0];
+  } else {
+    uint32_t phase = 0;
+    for (long long tile = tile_begin; tile < tile_end; ++tile) {
+      const long long s = tile * kTile + r;
+      const bool valid = s < total;
+      const float4 xr = s_row[r];
+      // ---- layer 0 on CUDA cores -> fp16 operand rows (this thread: features 16cg .. 16cg+15)
 #pragma unroll
-      for (int c = 0; c < CW; ++c) y += s_y[c][r];
-      if (a.out_f32) {
-        if (valid) a.out_f32[s] = y;
-      } else {
-        void* dst = a.out_ptrs[net_id];
-        if (a.out_dtype == 2) {
-          if (valid) reinterpret_cast<float*>(dst)[s] = y;
-        } else {  // inverse normalisation + truncating cast
-          const float vden = brief_denorm(n, y);
-          if (a.out_dtype == 1) {
-            if (full) s_out[r] = (unsigned short)(int)vden;
-            else if (valid) reinterpret_cast<unsigned short*>(dst)[s] = (unsigned short)(int)vden;
-          } else {
-            if (full) reinterpret_cast<unsigned char*>(s_out)[r] = (unsigned char)(int)vden;
-            else if (valid) reinterpret_cast<unsigned char*>(dst)[s] = (unsigned char)(int)vden;
+      for (int h = 0; h < 2; ++h) {
+        float z[8];
+        const uint4 pk = first_layer8<DUMP>(s_w0b, 16 * cg + 8 * h, xr.x, xr.y, xr.z, n.w0, z);
+        if (DUMP && valid)
+          for (int i = 0; i < 8; ++i)
+            if (16 * cg + 8 * h + i < n.f) a.layers_out[s * n.f + 16 * cg + 8 * h + i] = z[i];
+        *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * cg + h, kTile)) = pk;
+      }
+      signal();
+      float ypart = 0.f;
+      // ---- hidden layers on the tensor core
+      for (int l = 1; l <= NH; ++l) {
+        mbar_wait(&bar_mma, phase);
+        phase ^= 1;
+        tc_fence_after();
+        float v[16], th[16];
+        tmem_ld16(my_tmem, v);
+        tmem_ld_wait();
+        theta16(v, s_wb + (l - 1) * F + 16 * cg, th);
+        if (DUMP && valid) {
+          float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
+          for (int i = 0; i < 16; ++i)
+            if (16 * cg + i < n.f) zdump[16 * cg + i] = th[i] / wh;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
+        if (l < NH) {
+          store_chunk16(sAct, r, cg, v);
+          signal();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
+            ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
+            ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
           }
         }
       }
-      load_row(tile + 1);
-    }
-    __syncthreads();
-    // staged tile -> 16-byte vector stores (256 B contiguous for uint16)
-    if (!a.out_f32 && a.out_dtype != 2 && full) {
-      void* dst = a.out_ptrs[net_id];
-      if (a.out_dtype == 1) {
-        if (t < 16)
-          reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dst) + tile * kTile)[t] =
+      // ---- last layer: fixed-order sum of the column groups' partial dot products, then the output epilogue
+      s_y[cg][r] = ypart;
+      named_bar_sync(1, NT);
+      const bool full = tile * kTile + kTile <= total;
+      if (cg == 0) {
+        float y = s_bl[0];
+#pragma unroll
+        for (int c = 0; c < CW; ++c) y += s_y[c][r];
+        if (a.out_f32) {
+          if (valid) a.out_f32[s] = y;
+        } else {
+          void* dst = a.out_ptrs[net_id];
+          if (a.out_dtype == 2) {
+            if (valid) reinterpret_cast<float*>(dst)[s] = y;
+          } else {  // inverse normalisation + truncating cast
+            const float vden = brief_denorm(n, y);
+            if (a.out_dtype == 1) {
+              if (full) s_out[r] = (unsigned short)(int)vden;
+              else if (valid) reinterpret_cast<unsigned short*>(dst)[s] = (unsigned short)(int)vden;
+            } else {
+              if (full) reinterpret_cast<unsigned char*>(s_out)[r] = (unsigned char)(int)vden;
+              else if (valid) reinterpret_cast<unsigned char*>(dst)[s] = (unsigned char)(int)vden;
+            }
+          }
+        }
+        load_row(tile + 1);
+      }
+      named_bar_sync(1, NT);
+      // staged tile -> 16-byte vector stores (256 B contiguous for uint16)
+      if (!a.out_f32 && a.out_dtype != 2 && full) {
+        void* dst = a.out_ptrs[net_id];
+        if (a.out_dtype == 1) {
+          if (t < 16)
+            reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dst) + tile * kTile)[t] =
+                reinterpret_cast<const uint4*>(s_out)[t];
+        } else if (t < 8) {
+          reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + tile * kTile)[t] =
               reinterpret_cast<const uint4*>(s_out)[t];
-      } else if (t < 8) {
-        reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + tile * kTile)[t] =
-            reinterpret_cast<const uint4*>(s_out)[t];
+        }
       }
     }
   }
@@ -793,11 +813,11 @@ static cudaError_t launch_eval_f(const EvalArgs& a, int L_max, int n_blocks, cud
   if (a.layers_out) {
     e = cudaFuncSetAttribute(tc_eval_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, true><<<n_blocks, TcCfg<F>::THREADS, smem, st>>>(a);
+    tc_eval_kernel<F, true><<<n_blocks, TcCfg<F>::EVAL_THREADS, smem, st>>>(a);
   } else {
     e = cudaFuncSetAttribute(tc_eval_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, false><<<n_blocks, TcCfg<F>::THREADS, smem, st>>>(a);
+    tc_eval_kernel<F, false><<<n_blocks, TcCfg<F>::EVAL_THREADS, smem, st>>>(a);
   }
   return cudaGetLastError();
 }
