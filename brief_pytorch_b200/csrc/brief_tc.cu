@@ -394,7 +394,6 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   __shared__ __align__(16) float4 s_g[2][kTile];  // sampler staging: (x0, x1, x2, normalised target) per row
   __shared__ float s_gw[2][kTile];                //                  loss weight per row
   __shared__ float s_y[CW][kTile];
-  __shared__ float s_dy[kTile];
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -542,24 +541,20 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   auto loss_phase = [&](int tile) {
     s_y[cg][r] = ypart;
     epi_sync();
-    if (cg == 0) {
-      float y = s_bl[0];
+    // every thread of the row forms y, the error and dy itself (same operands, same order: identical values), so one
+    // barrier is enough; column group 0 additionally accumulates the loss and writes the dWlast operand block
+    float y = s_bl[0];
 #pragma unroll
-      for (int c = 0; c < CW; ++c) y += s_y[c][r];
-      float dys = 0.f;
-      if (s_begin + (long long)tile * kTile + r < s_end) {
-        const float e = y - xf.w;  // xf.w: the row's normalised target
-        const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : s_gw[tile & 1][r];
-        loss_acc = fmaf(wt * e, e, loss_acc);
-        dys = kGradScale * wt * e;
-      }
-      s_dy[r] = dys;
-      *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
+    for (int c = 0; c < CW; ++c) y += s_y[c][r];
+    float dys = 0.f;
+    if (s_begin + (long long)tile * kTile + r < s_end) {
+      const float e = y - xf.w;  // xf.w: the row's normalised target
+      const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : s_gw[tile & 1][r];
+      if (cg == 0) loss_acc = fmaf(wt * e, e, loss_acc);
+      dys = kGradScale * wt * e;
     }
-    epi_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_gfree[tile & 1]);  // staging slot consumed (coordinates live on in xf / xb)
-    const float dys = s_dy[r] * wh;
+    if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
+    dys *= wh;
     float dz[16];
 #pragma unroll
     for (int i = 0; i < 16; i += 4) {
@@ -568,6 +563,10 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
       dz[i + 2] = dys * w4.z * fast_cos(th[i + 2]); dz[i + 3] = dys * w4.w * fast_cos(th[i + 3]);
     }
     store_chunk16_sat(sDz, r, cg, dz);
+    // staging slot consumed (coordinates and target live on in xf / xb); s_y may be rewritten only after the next
+    // tile's forward pass, i.e. after many barriers
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_gfree[tile & 1]);
   };
   // ---- backward stage l of a tile.  issue: what the epilogue waits for (z_{l-1} recomputed, dX_{l-1}) is committed
   //      first; dW_l, db_l (+ dWlast at l == NH) follow and are tracked by the tile's next commit.
