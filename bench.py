@@ -52,6 +52,14 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic(name):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[name]["bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def plan_blocks(name):
     """Block grid + per-block width exactly as the reference sizes them (cal_divide_num, alloc_param 'equal' with
     by-size-equal blocks, SIREN.calc_features)."""
@@ -381,7 +389,8 @@ def main():
                             "per-block loss -> host"},
             "gpu_launches": int(launches_total),
             "roofline": {"bound": "tensor", "achieved": tf_kernel, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": tf_kernel / peak_tf, "traffic": None, "peak_src": pk["src"] + " bf16 burst",
+                         "frac": tf_kernel / peak_tf,
+                         "traffic": ncu_traffic(args.workload) if (world == 1 and prec == "f16") else None, "peak_src": pk["src"] + " bf16 burst",
                          "kernel": "fit (gather+fwd+loss+bwd)", "kernel_ms": 1e3 * t_kernel,
                          "flops_per_sample": fit_flops, "samples_per_launch": samples_per_step_local},
             "decompress": {"value": vox_total / t_dec, "unit": "voxels/s", "ms": 1e3 * t_dec,
