@@ -28,6 +28,17 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# Library banners (NCCL prints its version on fd 1) must not pollute the one-JSON-line contract: everything written to
+# stdout goes to stderr, and emit() writes the result line to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 METRIC = "siren_fit_coord_samples_per_s"
 UNIT = "coord-samples/s"
 
@@ -169,7 +180,7 @@ def run_reference(args, plan):
     dt = time.perf_counter() - t0
     val = plan["batch"] * args.steps / dt
     sample = f"one block ({'x'.join(map(str, plan['block_shape']))}, f={plan['features']}) per step, batch {plan['batch']}"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -412,7 +423,7 @@ def main():
             line["cpu_baseline"] = {"value": plan["batch"] * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n} steps of one block (f={plan['features']}, batch {plan['batch']}) "
                                               f"with the oracle's torch-CPU restatement of main.py:385-400"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -32,6 +32,7 @@
 // Roofline: per sample a hidden layer costs 2*F*F tensor FLOPs and F special-function ops (2F in the fit).  At
 // F <= 64 the MUFU pipe (16 ops/clk/SM), not the tensor pipe, is the binding unit.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "brief_common.cuh"
 #include "brief_kernels.h"
@@ -40,6 +41,17 @@
 namespace brief {
 
 using namespace umma;
+
+// ---- optional stage timing (tools/tc_stage_timing.py builds a second library with -DBRIEF_TC_TIMING) ----------------
+#ifdef BRIEF_TC_TIMING
+__device__ unsigned long long g_tc_timing[64];
+#define TT(var) const long long var = clock64()
+#define TACC(slot, expr) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp >= NW)) \
+    atomicAdd(&g_tc_timing[(slot) + (warp == 0 ? 0 : warp == NW ? 16 : 32)], (unsigned long long)(expr)); } while (0)
+#else
+#define TT(var)
+#define TACC(slot, expr)
+#endif
 
 constexpr int kTile = 128;
 constexpr int kEvalTilesPerBlock = 64;     // must match kTcEvalTilesPerBlock in brief_capi.cu
@@ -73,8 +85,13 @@ __device__ __forceinline__ void tc_load_net(NetDev& dst, const NetDev& src) {
 
 // sin / cos on the special-function unit (MUFU after the 1/2pi pre-scale); abs error ~1e-6 for |theta| < 64, far
 // below the fp16 rounding of the activation it feeds
+#ifdef BRIEF_EXP_NOSIN  // experiment only (tools/exp_variant.py): what does the kernel cost without the SFU work?
+__device__ __forceinline__ float fast_sin(float x) { return x * 0.159f; }
+__device__ __forceinline__ float fast_cos(float x) { return x * 0.161f; }
+#else
 __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
 __device__ __forceinline__ float fast_cos(float x) { return __cosf(x); }
+#endif
 
 // first layer for 8 consecutive features of one sample -> 4 packed f16x2 words (optionally the raw z)
 template <bool WITH_Z>
@@ -130,9 +147,7 @@ template <int F>
 struct TcCfg {
   static constexpr int CW = F / 16;
   static constexpr int THREADS = 128 * CW;                                // epilogue threads
-  static constexpr int EVAL_THREADS = THREADS + 32;                       // + one warp that only issues MMAs
   static constexpr int FIT_THREADS = THREADS + 64;                        // + MMA-issue warp + sampler warp
-  static constexpr int EVAL_MIN_BLOCKS = F >= 48 ? 2 : F == 32 ? 4 : 8;  // ~1024 threads per SM
   static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 4;    // must match tc_fit_ctas_per_sm()
 };
 
@@ -164,22 +179,35 @@ __device__ __forceinline__ void theta16(const float* wz, const float* __restrict
 // ==================================================================================================================
 // forward / decompress
 // ==================================================================================================================
-template <int F, bool DUMP>
-__global__ void __launch_bounds__(TcCfg<F>::EVAL_THREADS, TcCfg<F>::EVAL_MIN_BLOCKS) tc_eval_kernel(EvalArgs a) {
-  constexpr int CW = TcCfg<F>::CW;
-  constexpr int NT = TcCfg<F>::THREADS;  // epilogue threads; warp NW only issues MMAs (see the fit kernel)
+// CH = 16-column chunks per thread: the CTA has 128 * F/16/CH epilogue threads (+ the MMA warp).  Fewer, fatter threads
+// leave room for MORE resident CTAs per SM, i.e. more independent tiles whose MMA latency and store/fence tails hide
+// under each other's sines.
+template <int F, int CH>
+struct EvalCfg {
+  static constexpr int CWG = F / 16 / CH;            // column groups = epilogue warps per TMEM lane quadrant
+  static constexpr int NT = 128 * CWG;               // epilogue threads
+  static constexpr int THREADS = NT + 32;            // + one warp that only issues MMAs
+  static constexpr int REGS = CH == 1 ? 56 : CH == 2 ? 72 : 96;  // register budget per thread the bound leaves
+  static constexpr int MIN_BLOCKS = 65536 / (THREADS * REGS) < 1 ? 1 : 65536 / (THREADS * REGS) > 8 ? 8 : 65536 / (THREADS * REGS);
+};
+
+template <int F, int CH, bool DUMP>
+__global__ void __launch_bounds__(EvalCfg<F, CH>::THREADS, EvalCfg<F, CH>::MIN_BLOCKS) tc_eval_kernel(EvalArgs a) {
+  constexpr int CWG = EvalCfg<F, CH>::CWG;
+  constexpr int NT = EvalCfg<F, CH>::NT;  // epilogue threads; warp NW only issues MMAs (see the fit kernel)
   constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
   __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_r;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float4 s_row[kTile];
-  __shared__ float s_y[CW][kTile];
+  __shared__ float s_y[CWG][kTile];
   __shared__ __align__(16) unsigned short s_out[kTile];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const bool mma_warp = warp == NW;
-  const int q = warp & 3, cg = mma_warp ? CW : (warp >> 2), r = 32 * q + lane;
+  const int q = warp & 3, cg = mma_warp ? 0 : (warp >> 2), r = 32 * q + lane;
+  const int c_base = cg * CH;  // first 16-column chunk of this thread
   int net_id;
   long long chunk;
   if (a.single_net >= 0) {
@@ -217,7 +245,7 @@ __global__ void __launch_bounds__(TcCfg<F>::EVAL_THREADS, TcCfg<F>::EVAL_MIN_BLO
     bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
   }
   const uint32_t tm = tmem_base_s;
-  const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * cg;
+  const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * c_base;
   const uint32_t aAct = smem_u32(sAct), aW = smem_u32(sW);
   const long long total = a.coords ? a.n_coords : n.n_vox;
   const long long n_tiles = (total + kTile - 1) / kTile;
@@ -245,7 +273,7 @@ __global__ void __launch_bounds__(TcCfg<F>::EVAL_THREADS, TcCfg<F>::EVAL_MIN_BLO
     __syncwarp();
     if (lane == 0) mbar_arrive(&bar_r);
   };
-  if (cg == 0) load_row(tile_begin);
+  if (!mma_warp && cg == 0) load_row(tile_begin);
   mbar_wait(&bar_w, 0);
   __syncthreads();
 
@@ -253,69 +281,95 @@ __global__ void __launch_bounds__(TcCfg<F>::EVAL_THREADS, TcCfg<F>::EVAL_MIN_BLO
     uint32_t ph_r = 0;
     for (long long tile = tile_begin; tile < tile_end; ++tile)
       for (int l = 1; l <= NH; ++l) {
+        TT(m0);
         mbar_wait(&bar_r, ph_r);
         ph_r ^= 1;
         tc_fence_after();
+        TT(m1);
         if (elect_one()) {
           issue_forward<F>(tm, aAct, aW + (uint32_t)(l - 1) * F * F * 2);
           commit(&bar_mma);
         }
         __syncwarp();
+        TT(m2);
+        TACC(0, m1 - m0); TACC(1, m2 - m1); TACC(7, 1);
       }
   } else {
     uint32_t phase = 0;
     for (long long tile = tile_begin; tile < tile_end; ++tile) {
       const long long s = tile * kTile + r;
       const bool valid = s < total;
+      TT(e0);
       const float4 xr = s_row[r];
-      // ---- layer 0 on CUDA cores -> fp16 operand rows (this thread: features 16cg .. 16cg+15)
+      // ---- layer 0 on CUDA cores -> fp16 operand rows (this thread: features 16 c_base .. 16 (c_base + CH) - 1)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < 2 * CH; ++h) {
         float z[8];
-        const uint4 pk = first_layer8<DUMP>(s_w0b, 16 * cg + 8 * h, xr.x, xr.y, xr.z, n.w0, z);
+        const uint4 pk = first_layer8<DUMP>(s_w0b, 16 * c_base + 8 * h, xr.x, xr.y, xr.z, n.w0, z);
         if (DUMP && valid)
           for (int i = 0; i < 8; ++i)
-            if (16 * cg + 8 * h + i < n.f) a.layers_out[s * n.f + 16 * cg + 8 * h + i] = z[i];
-        *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * cg + h, kTile)) = pk;
+            if (16 * c_base + 8 * h + i < n.f) a.layers_out[s * n.f + 16 * c_base + 8 * h + i] = z[i];
+        *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * c_base + h, kTile)) = pk;
       }
+      TT(e1);
       signal();
+      TT(e2);
+      TACC(0, e1 - e0); TACC(1, e2 - e1);
       float ypart = 0.f;
       // ---- hidden layers on the tensor core
       for (int l = 1; l <= NH; ++l) {
+        TT(e3);
         mbar_wait(&bar_mma, phase);
         phase ^= 1;
         tc_fence_after();
-        float v[16], th[16];
-        tmem_ld16(my_tmem, v);
+        TT(e4);
+        float v[CH][16];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) tmem_ld16(my_tmem + 16 * c, v[c]);
         tmem_ld_wait();
-        theta16(v, s_wb + (l - 1) * F + 16 * cg, th);
-        if (DUMP && valid) {
-          float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
-          for (int i = 0; i < 16; ++i)
-            if (16 * cg + i < n.f) zdump[16 * cg + i] = th[i] / wh;
-        }
+        TT(e5);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
-        if (l < NH) {
-          store_chunk16(sAct, r, cg, v);
-          signal();
-        } else {
+        for (int c = 0; c < CH; ++c) {
+          float th[16];
+          theta16(v[c], s_wb + (l - 1) * F + 16 * (c_base + c), th);
+          if (DUMP && valid) {
+            float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
+            for (int i = 0; i < 16; ++i)
+              if (16 * (c_base + c) + i < n.f) zdump[16 * (c_base + c) + i] = th[i] / wh;
+          }
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
-            ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
-            ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
+          for (int i = 0; i < 16; ++i) v[c][i] = fast_sin(th[i]);
+          if (l < NH) {
+            store_chunk16(sAct, r, c_base + c, v[c]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
+              ypart = fmaf(w4.x, v[c][i], ypart); ypart = fmaf(w4.y, v[c][i + 1], ypart);
+              ypart = fmaf(w4.z, v[c][i + 2], ypart); ypart = fmaf(w4.w, v[c][i + 3], ypart);
+            }
           }
         }
+        TT(e6);
+        if (l < NH) signal();
+        TT(e7);
+        TACC(2, e4 - e3); TACC(3, e5 - e4); TACC(4, e6 - e5); TACC(5, e7 - e6);
       }
+      TT(e8);
       // ---- last layer: fixed-order sum of the column groups' partial dot products, then the output epilogue
-      s_y[cg][r] = ypart;
-      named_bar_sync(1, NT);
       const bool full = tile * kTile + kTile <= total;
+      float y = ypart;
+      if (CWG > 1) {
+        s_y[cg][r] = ypart;
+        named_bar_sync(1, NT);
+      }
       if (cg == 0) {
-        float y = s_bl[0];
+        if (CWG > 1) {
+          y = 0.f;
 #pragma unroll
-        for (int c = 0; c < CW; ++c) y += s_y[c][r];
+          for (int c = 0; c < CWG; ++c) y += s_y[c][r];
+        }
+        y += s_bl[0];
         if (a.out_f32) {
           if (valid) a.out_f32[s] = y;
         } else {
@@ -348,6 +402,8 @@ __global__ void __launch_bounds__(TcCfg<F>::EVAL_THREADS, TcCfg<F>::EVAL_MIN_BLO
               reinterpret_cast<const uint4*>(s_out)[t];
         }
       }
+      TT(e9);
+      TACC(6, e9 - e8); TACC(7, e9 - e0); TACC(8, 1);
     }
   }
   tc_fence_before();
@@ -619,22 +675,29 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
         __syncwarp();
       }
     }
+    TT(m_start);
     for (int i = 0; i < n_tiles; ++i) {
       const int pa = i & 1, pb = pa ^ 1;
       const bool has_b = i + 1 < n_tiles;
+      TT(m0);
       mbar_wait(&bar_ra, ph_ra);  // dz_NH / sDY of tile i and a_0 / sX of tile i+1 are in place
       ph_ra ^= 1;
       tc_fence_after();
+      TT(m1);
       if (elect_one()) {
         issue_bwd(pa, NH, i > 0);
         if (has_b) issue_fwd(pb, 1);
       }
       __syncwarp();
+      TT(m2);
+      TACC(0, m1 - m0); TACC(1, m2 - m1);
       for (int j = 1; j <= NH; ++j) {
         const int l = NH + 1 - j;
+        TT(m3);
         mbar_wait(&bar_ra, ph_ra);  // dz_{l-1} written
         ph_ra ^= 1;
         tc_fence_after();
+        TT(m4);
         cur ^= 1;  // mirrors bwd_epilogue's buffer flip
         if (elect_one()) {
           if (l > 1) {
@@ -645,23 +708,33 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
           }
         }
         __syncwarp();
+        TT(m5);
+        TACC(2, m4 - m3); TACC(3, m5 - m4);
         if (has_b && j < NH) {
           mbar_wait(&bar_rb, ph_rb);  // a_j written
           ph_rb ^= 1;
           tc_fence_after();
+          TT(m6);
           if (elect_one()) issue_fwd(pb, j + 1);
           __syncwarp();
+          TT(m7);
+          TACC(4, m6 - m5); TACC(5, m7 - m6);
         }
       }
       cur = 0;
     }
+    { TT(m_end); TACC(6, m_end - m_start); TACC(7, n_tiles); }
   } else if (sampler_warp) {
     // ---- the sampler warp runs up to two tiles ahead of the epilogue warps
     for (int k = 0; k < n_tiles; ++k) {
+      TT(g0);
       if (k >= 2) mbar_wait(&bar_gfree[k & 1], (uint32_t)((k >> 1) - 1) & 1);
+      TT(g1);
       sample_tile(k, k & 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_gfull[k & 1]);
+      TT(g2);
+      TACC(0, g1 - g0); TACC(1, g2 - g1); TACC(7, 1);
     }
   } else {
     // ---- epilogue warps
@@ -680,37 +753,53 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
       xb = xf;
       cur = 0;
     }
+    TT(e_start);
     for (int i = 0; i < n_tiles; ++i) {  // tile i walks backward, tile i+1 forward (ring parity pb)
       const int pb = (i & 1) ^ 1;
       const bool has_b = i + 1 < n_tiles;
+      TT(e0);
       if (has_b) fwd_prologue(i + 1);
       signal(&bar_ra);
+      TT(e1);
+      TACC(0, e1 - e0);
       for (int j = 1; j <= NH; ++j) {
         const int l = NH + 1 - j;
         // -- backward tile
+        TT(e2);
         mbar_wait(&bar_a, ph_a);
         ph_a ^= 1;
         tc_fence_after();
+        TT(e3);
         bwd_epilogue(l);
         signal(&bar_ra);
+        TT(e4);
+        TACC(1, e3 - e2); TACC(2, e4 - e3);
         // -- forward tile
         if (has_b) {
           mbar_wait(&bar_b, ph_b);
           ph_b ^= 1;
           tc_fence_after();
+          TT(e5);
           fwd_epilogue(pb, j);
           if (j < NH) signal(&bar_rb);
+          TT(e6);
+          TACC(3, e5 - e4); TACC(4, e6 - e5);
         }
       }
+      TT(e7);
       mbar_wait(&bar_a, ph_a);  // tile i is done: its ring slots, sX and sDz may be reused
       ph_a ^= 1;
       tc_fence_after();
+      TT(e8);
       if (has_b) {
         loss_phase(i + 1);
         xb = xf;
         cur = 0;
       }
+      TT(e9);
+      TACC(5, e8 - e7); TACC(6, e9 - e8);
     }
+    { TT(e_end); TACC(7, e_end - e_start); TACC(8, n_tiles); }
   }
   __syncthreads();
 
@@ -805,28 +894,41 @@ bool tc_supported(int f, int L, int in_dim, int out_dim) {
   return true;
 }
 
-template <int F>
-static cudaError_t launch_eval_f(const EvalArgs& a, int L_max, int n_blocks, cudaStream_t st) {
+template <int F, int CH>
+static cudaError_t launch_eval_fc(const EvalArgs& a, int L_max, int n_blocks, cudaStream_t st) {
   const size_t smem = tc_eval_smem(F, L_max);
   cudaError_t e;
   if (a.layers_out) {
-    e = cudaFuncSetAttribute(tc_eval_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(tc_eval_kernel<F, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, true><<<n_blocks, TcCfg<F>::EVAL_THREADS, smem, st>>>(a);
+    tc_eval_kernel<F, CH, true><<<n_blocks, EvalCfg<F, CH>::THREADS, smem, st>>>(a);
   } else {
-    e = cudaFuncSetAttribute(tc_eval_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(tc_eval_kernel<F, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, false><<<n_blocks, TcCfg<F>::EVAL_THREADS, smem, st>>>(a);
+    tc_eval_kernel<F, CH, false><<<n_blocks, EvalCfg<F, CH>::THREADS, smem, st>>>(a);
   }
   return cudaGetLastError();
 }
 
+// chunks per thread: default per width, BRIEF_EVAL_CH overrides (tuning)
+static int eval_ch(int F) {
+  static const int env = [] { const char* e = getenv("BRIEF_EVAL_CH"); return e ? atoi(e) : 0; }();
+  const int n = F / 16;
+  if (env > 0 && n % env == 0) return env;
+  return F == 64 ? 2 : F == 48 ? 3 : F == 32 ? 2 : 1;
+}
+
 cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st) {
-  switch (F_PAD) {
-    case 16: return launch_eval_f<16>(a, L_max, n_blocks, st);
-    case 32: return launch_eval_f<32>(a, L_max, n_blocks, st);
-    case 48: return launch_eval_f<48>(a, L_max, n_blocks, st);
-    case 64: return launch_eval_f<64>(a, L_max, n_blocks, st);
+  const int ch = eval_ch(F_PAD);
+  switch (F_PAD * 8 + ch) {
+    case 16 * 8 + 1: return launch_eval_fc<16, 1>(a, L_max, n_blocks, st);
+    case 32 * 8 + 1: return launch_eval_fc<32, 1>(a, L_max, n_blocks, st);
+    case 32 * 8 + 2: return launch_eval_fc<32, 2>(a, L_max, n_blocks, st);
+    case 48 * 8 + 1: return launch_eval_fc<48, 1>(a, L_max, n_blocks, st);
+    case 48 * 8 + 3: return launch_eval_fc<48, 3>(a, L_max, n_blocks, st);
+    case 64 * 8 + 1: return launch_eval_fc<64, 1>(a, L_max, n_blocks, st);
+    case 64 * 8 + 2: return launch_eval_fc<64, 2>(a, L_max, n_blocks, st);
+    case 64 * 8 + 4: return launch_eval_fc<64, 4>(a, L_max, n_blocks, st);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -852,4 +954,12 @@ cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int L_max, int n_blocks, 
 }
 
 }  // namespace brief
+
+#ifdef BRIEF_TC_TIMING
+extern "C" int brief_debug_read_timing(unsigned long long* out, int reset) {
+  cudaMemcpyFromSymbol(out, brief::g_tc_timing, sizeof(unsigned long long) * 64);
+  if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(brief::g_tc_timing, z, sizeof z); }
+  return 0;
+}
+#endif
 
