@@ -16,6 +16,7 @@
 // plus 4 B/param/slice of partial traffic; HBM/L2-bound and tiny next to the fit kernel.
 #include "brief_common.cuh"
 #include "brief_kernels.h"
+#include "brief_image.cuh"
 #include <cuda_fp16.h>
 
 namespace brief {
@@ -86,43 +87,68 @@ cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-// ---- fp16 operand image for the tcgen05 kernels ----------------------------------------------------
-// Image of network n (bytes, at wpack + n.wpack_off), F = F_PAD, NH = L-2:
-//   [NH] hidden weights TIMES w_hidden, fp16, UMMA no-swizzle core-matrix layout: element (o,k) of layer l at
-//        l*F*F*2 + ((k/8)*(F/8) + o/8)*128 + (o%8)*16 + (k%8)*2       (8x8 cores, K contiguous)
-//   then fp32: first layer float4 (wx,wy,wz,b0) x F | omega*bias [NH][F] | Wlast [F] | blast,0,0,0
-// Pad column f (the first unused feature) is the constant-one feature of the fit kernel: its weights are zero
-// and its "bias" makes the sine argument pi/2, so every activation buffer carries a 1.0 in column f and the
-// bias gradients fall out of the dW contractions.
+// ---- fp16 operand image for the tcgen05 kernels (layout: brief_image.cuh) -----------------------------------------
+__device__ __forceinline__ __half hi16(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ __half lo16(float x) { return __float2half_rn(__fsub_rn(x, __half2float(__float2half_rn(x)))); }
+
 __global__ void pack_kernel(const NetDev* nets, int n_nets, const float* __restrict__ params, unsigned char* wpack) {
+  constexpr float kHalfPi = 1.57079632679f;
   for (int net_id = blockIdx.y; net_id < n_nets; net_id += gridDim.y) {
   const NetDev& n = nets[net_id];
   if (n.prec != 1) continue;
   const int F = n.F_PAD, NH = n.L - 2, f = n.f, F4 = n.F4;
   const float* P = params + n.param_off;
   unsigned char* img = wpack + n.wpack_off;
-  const int n_hidden = NH * F * F;
-  const int n_side = 4 * F + NH * F + F + 4;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hidden + n_side; i += gridDim.x * blockDim.x) {
+  const int n_hidden = NH * F * F, n_l0 = F * 16, n_last = 16 * F;
+  const int n_side = (int)img_side_floats(F, NH);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_hidden + n_l0 + n_last + n_side; i += gridDim.x * blockDim.x) {
     if (i < n_hidden) {
       const int l = i / (F * F), r = i - l * F * F;
       const int o = r / F, k = r - o * F;
-      // hidden weights are stored pre-multiplied by the hidden omega: the MMA then yields w*z directly, and the dX
-      // contraction yields w * dz W, which is the factor the chain rule needs (one FMUL less per element)
-      const float w = (o < f && k < f) ? __fmul_rn(n.wh, P[dl_W(n, l + 1) + o * F4 + k]) : 0.f;
-      const size_t off = (size_t)l * F * F * 2 + ((size_t)(k >> 3) * (F >> 3) + (o >> 3)) * 128 + (o & 7) * 16 + (k & 7) * 2;
-      *reinterpret_cast<__half*>(img + off) = __float2half_rn(w);
+      // hidden weights are stored pre-multiplied by the hidden omega: the MMA then yields the sine argument directly
+      // (bias included, through the two constant-one columns), and the dX contraction yields w * dz W
+      __half h = __float2half_rn(0.f);
+      if (o < f) {
+        if (k < f) h = hi16(__fmul_rn(n.wh, P[dl_W(n, l + 1) + o * F4 + k]));
+        else if (k == f) h = hi16(__fmul_rn(n.wh, P[dl_b(n, l + 1) + o]));
+        else if (k == f + 1) h = lo16(__fmul_rn(n.wh, P[dl_b(n, l + 1) + o]));
+      } else if (o <= f + 1) {
+        if (k == f) h = hi16(kHalfPi);
+        else if (k == f + 1) h = lo16(kHalfPi);
+      }
+      *reinterpret_cast<__half*>(img + (size_t)l * F * F * 2 + img_elem_off(o, k, F)) = h;
+    } else if (i < n_hidden + n_l0) {
+      const int r = i - n_hidden, o = r >> 4, c = r & 15;
+      __half h = __float2half_rn(0.f);
+      if (o < f) {
+        const int d = c & 3;
+        const float v = d < 3 ? __fmul_rn(n.w0, P[dl_W0(n) + 4 * o + d]) : __fmul_rn(n.w0, P[dl_b0(n) + o]);
+        if (c < 3 || c == 3 || (c >= 4 && c < 7)) h = hi16(v);
+        else if (c == 7 || (c >= 8 && c < 11)) h = lo16(v);
+      } else if (o <= f + 1) {
+        if (c == 3) h = hi16(kHalfPi);
+        else if (c == 7) h = lo16(kHalfPi);
+      }
+      *reinterpret_cast<__half*>(img + img_l0_off(F, NH) + img_elem_off(o, c, F)) = h;
+    } else if (i < n_hidden + n_l0 + n_last) {
+      const int q = i - n_hidden - n_l0, r = q / F, k = q - r * F;
+      __half h = __float2half_rn(0.f);
+      if (r < 2 && k <= f) {
+        const float v = k < f ? P[dl_Wlast(n) + k] : P[dl_blast(n)];
+        h = r == 0 ? hi16(v) : lo16(v);
+      }
+      *reinterpret_cast<__half*>(img + img_last_off(F, NH) + img_elem_off(r, k, 16)) = h;
     } else {
-      const int j = i - n_hidden;
-      float* side = reinterpret_cast<float*>(img + (size_t)n_hidden * 2);
+      const int j = i - n_hidden - n_l0 - n_last;
+      float* side = reinterpret_cast<float*>(img + img_side_off(F, NH));
       float val;
       if (j < 4 * F) {
         const int o = j >> 2, c = j & 3;
         val = (o < f) ? (c < 3 ? P[dl_W0(n) + 4 * o + c] : P[dl_b0(n) + o])
-                      : (o == f && c == 3 ? __fdiv_rn(1.57079632679f, n.w0) : 0.f);
+                      : (o <= f + 1 && c == 3 ? __fdiv_rn(kHalfPi, n.w0) : 0.f);
       } else if (j < 4 * F + NH * F) {
         const int q = j - 4 * F, l = q / F, o = q - l * F;
-        val = (o < f) ? __fmul_rn(n.wh, P[dl_b(n, l + 1) + o]) : (o == f ? 1.57079632679f : 0.f);
+        val = (o < f) ? __fmul_rn(n.wh, P[dl_b(n, l + 1) + o]) : (o <= f + 1 ? kHalfPi : 0.f);
       } else if (j < 4 * F + NH * F + F) {
         const int k = j - 4 * F - NH * F;
         val = (k < f) ? P[dl_Wlast(n) + k] : 0.f;

@@ -35,6 +35,7 @@
 #include <cstdlib>
 
 #include "brief_common.cuh"
+#include "brief_image.cuh"
 #include "brief_kernels.h"
 #include "brief_umma.cuh"
 
@@ -60,14 +61,7 @@ constexpr uint32_t kActLBO = (kTile / 8) * 128;  // 2048: feature-group stride o
 
 __host__ __device__ constexpr int tmem_cols_pow2(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-// ---- packed image (written by pack_kernel, brief_opt.cu) ------------------------------------------------------
-//   [NH][F*F] fp16 hidden weights times w_hidden (interleaved, R = F)  |  fp32 side block:
-//   float4 (W0x, W0y, W0z, b0) x F | w_hidden * b_l [NH][F] | Wlast [F] | blast, 0, 0, 0
-__host__ __device__ constexpr size_t img_hidden_bytes(int F, int NH) { return (size_t)NH * F * F * 2; }
-__host__ __device__ constexpr size_t img_side_floats(int F, int NH) { return (size_t)4 * F + (size_t)NH * F + F + 4; }
-__host__ __device__ constexpr size_t img_bytes(int F, int NH) { return img_hidden_bytes(F, NH) + img_side_floats(F, NH) * 4; }
-__host__ __device__ constexpr size_t img_bytes_padded(int F, int NH) { return (img_bytes(F, NH) + 127) & ~(size_t)127; }
-
+// ---- packed image: brief_image.cuh (written by pack_kernel, brief_opt.cu) --------------------------------------------
 __device__ __forceinline__ int tc_find_work(const int* __restrict__ prefix, int n, int b) {
   int lo = 0, hi = n;
   while (hi - lo > 1) {
@@ -166,16 +160,6 @@ __device__ __forceinline__ void store_chunk16_sat(unsigned char* buf, int r, int
                  pack_f16x2_sat(v[14], v[15]));
 }
 
-// theta_i = (w z)_i + (w b)_i for the thread's 16 columns (the packed weights already carry the hidden omega)
-__device__ __forceinline__ void theta16(const float* wz, const float* __restrict__ wb, float* th) {
-#pragma unroll
-  for (int i = 0; i < 16; i += 4) {
-    const float4 b4 = *reinterpret_cast<const float4*>(wb + i);
-    th[i] = wz[i] + b4.x; th[i + 1] = wz[i + 1] + b4.y;
-    th[i + 2] = wz[i + 2] + b4.z; th[i + 3] = wz[i + 3] + b4.w;
-  }
-}
-
 // ==================================================================================================================
 // forward / decompress
 // ==================================================================================================================
@@ -233,7 +217,7 @@ __global__ void __launch_bounds__(EvalCfg<F, CH>::THREADS, EvalCfg<F, CH>::MIN_B
   const NetDev& n = sn;
   const int NH = n.L - 2;
   unsigned char* sW = smem;                                             // packed image (hidden weights + side)
-  const float* side = reinterpret_cast<const float*>(sW + img_hidden_bytes(F, NH));
+  const float* side = reinterpret_cast<const float*>(sW + img_side_off(F, NH));
   const float4* s_w0b = reinterpret_cast<const float4*>(side);          // [F]
   const float* s_wb = side + 4 * F;                                     // [NH][F]
   const float* s_wl = s_wb + NH * F;                                    // [F]
@@ -330,15 +314,14 @@ __global__ void __launch_bounds__(EvalCfg<F, CH>::THREADS, EvalCfg<F, CH>::MIN_B
         TT(e5);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          float th[16];
-          theta16(v[c], s_wb + (l - 1) * F + 16 * (c_base + c), th);
+          const float* th = v[c];  // the packed weights carry omega and the bias: the accumulator IS the sine argument
           if (DUMP && valid) {
             float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
             for (int i = 0; i < 16; ++i)
               if (16 * (c_base + c) + i < n.f) zdump[16 * (c_base + c) + i] = th[i] / wh;
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[c][i] = fast_sin(th[i]);
+          for (int i = 0; i < 16; ++i) v[c][i] = fast_sin(v[c][i]);
           if (l < NH) {
             store_chunk16(sAct, r, c_base + c, v[c]);
           } else {
@@ -486,7 +469,7 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   unsigned char* sX = sRing + (size_t)R * BUF;
   unsigned char* sDY = sX + 2 * BLK;
   unsigned char* sW = sDY + BLK;
-  const float* side = reinterpret_cast<const float*>(sW + img_hidden_bytes(F, NH));
+  const float* side = reinterpret_cast<const float*>(sW + img_side_off(F, NH));
   const float4* s_w0b = reinterpret_cast<const float4*>(side);
   const float* s_wb = side + 4 * F;
   const float* s_wl = s_wb + NH * F;
@@ -577,9 +560,8 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   };
   auto fwd_epilogue = [&](int parity, int j) {
     float v[16];
-    tmem_ld16(my_tmem, v);
+    tmem_ld16(my_tmem, th);  // the packed weights carry omega and the bias: the accumulator IS the sine argument
     tmem_ld_wait();
-    theta16(v, s_wb + (j - 1) * F + 16 * cg, th);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
     store_chunk16(sRing + slot(parity, j), r, cg, v);
@@ -642,9 +624,8 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
       tmem_ld16(my_tmem + F, vz);
       tmem_ld16(my_tmem + 2 * F, vx);
       tmem_ld_wait();
-      theta16(vz, s_wb + (l - 2) * F + 16 * cg, dz);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dz[i] = vx[i] * fast_cos(dz[i]);  // vx = w * (dz_l W_l): omega-scaled weights
+      for (int i = 0; i < 16; ++i) dz[i] = vx[i] * fast_cos(vz[i]);  // vx = w * (dz_l W_l): omega-scaled weights
     } else {  // layer 0: z_0 recomputed on CUDA cores from the backward tile's coordinates
       const float w0_over_wh = w0 / wh;
       tmem_ld16(my_tmem + 2 * F, vx);
@@ -866,7 +847,7 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
 // ==================================================================================================================
 // host side
 // ==================================================================================================================
-int tc_fpad(int f) { return ((f + 1 + 15) / 16) * 16; }
+int tc_fpad(int f) { return ((f + 2 + 15) / 16) * 16; }  // two constant-one columns (bias hi / lo)
 
 size_t tc_wpack_bytes(int F, int L) { return img_bytes(F, L - 2); }
 size_t tc_eval_smem(int F, int L) { return img_bytes_padded(F, L - 2) + (size_t)kTile * F * 2; }
