@@ -52,7 +52,12 @@ int fail(int code, const char* fmt, ...) {
 constexpr size_t kSmemLimit = 200 * 1024;       // dynamic smem budget of the fp32 kernels
 constexpr size_t kPartialCapBytes = 16u << 20;  // gradient-partial budget per network
 constexpr int kTcTile = 128;                    // samples per tcgen05 tile (UMMA M)
-constexpr int kTcEvalTilesPerBlock = 64;
+// tiles per decompress CTA: a multiple of 8 (the kernel's tile slots), sized for >= ~4 CTAs per SM when the work allows
+int tc_eval_tpb(long long total_tiles, int num_sms) {
+  long long t = total_tiles / (4LL * num_sms);
+  t = (t + 7) / 8 * 8;
+  return (int)std::min<long long>(128, std::max<long long>(8, t));
+}
 constexpr int kBuckets = 9;  // F_PAD / 16 in 1..8
 
 template <class T>
@@ -107,6 +112,7 @@ struct BriefGroup {
   int simt_eval_tm = 0;
   size_t simt_eval_smem = 0;
   WorkTable simt_eval, tc_eval[kBuckets];
+  int tc_eval_tpb[kBuckets] = {0};  // decompress tiles per CTA, per bucket
   int tc_L[kBuckets] = {0};  // deepest network per tensor-core bucket (sizes the dynamic shared memory)
 };
 
@@ -200,12 +206,16 @@ int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   g->simt_eval_smem = 0;
   std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets];
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
+  long long bucket_tiles[kBuckets] = {0};
+  for (const auto& n : g->nets)
+    if (n.prec == BRIEF_PREC_F16) bucket_tiles[n.F_PAD / 16] += (n.n_vox + kTcTile - 1) / kTcTile;
+  for (int b = 1; b < kBuckets; ++b) g->tc_eval_tpb[b] = tc_eval_tpb(bucket_tiles[b], g->num_sms);
   for (int i = 0; i < g->n_nets; ++i) {
     const NetDev& n = g->nets[i];
     if (n.prec == BRIEF_PREC_F16) {
       const int b = n.F_PAD / 16;
       const long long tiles = (n.n_vox + kTcTile - 1) / kTcTile;
-      const long long blocks = (tiles + kTcEvalTilesPerBlock - 1) / kTcEvalTilesPerBlock;
+      const long long blocks = (tiles + g->tc_eval_tpb[b] - 1) / g->tc_eval_tpb[b];
       if (tp[b].back() + blocks > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "group too large for one launch");
       tn[b].push_back(i);
       tp[b].push_back((int)(tp[b].back() + blocks));
@@ -719,7 +729,8 @@ int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n
   if (nd.prec == BRIEF_PREC_F16) {
     RC(ensure_wpack(g, st));
     const long long tiles = (n + kTcTile - 1) / kTcTile;
-    const long long blocks = (tiles + kTcEvalTilesPerBlock - 1) / kTcEvalTilesPerBlock;
+    a.tiles_per_block = tc_eval_tpb(tiles, g->num_sms);
+    const long long blocks = (tiles + a.tiles_per_block - 1) / a.tiles_per_block;
     a.TM = kTcTile;
     LAUNCH(launch_tc_eval(a, nd.F_PAD, nd.L, (int)blocks, st));
   } else {
@@ -766,6 +777,7 @@ int brief_decompress(BriefGroup* g, void* const* host_dev_out, int32_t out_dtype
     a.work_net = g->d_eval_tables.p + g->tc_eval[b].off_net;
     a.n_work = g->tc_eval[b].n;
     a.TM = kTcTile;
+    a.tiles_per_block = g->tc_eval_tpb[b];
     LAUNCH(launch_tc_eval(a, 16 * b, g->tc_L[b], g->tc_eval[b].blocks, st));
   }
   return 0;

@@ -55,7 +55,6 @@ __device__ unsigned long long g_tc_timing[64];
 #endif
 
 constexpr int kTile = 128;
-constexpr int kEvalTilesPerBlock = 64;     // must match kTcEvalTilesPerBlock in brief_capi.cu
 constexpr float kGradScale = 1.0f / 256.0f;  // dy' = kGradScale * w * (yhat - y)
 constexpr uint32_t kActLBO = (kTile / 8) * 128;  // 2048: feature-group stride of a [128 x F] operand buffer
 
@@ -163,35 +162,36 @@ __device__ __forceinline__ void store_chunk16_sat(unsigned char* buf, int r, int
 // ==================================================================================================================
 // forward / decompress
 // ==================================================================================================================
-// CH = 16-column chunks per thread: the CTA has 128 * F/16/CH epilogue threads (+ the MMA warp).  Fewer, fatter threads
-// leave room for MORE resident CTAs per SM, i.e. more independent tiles whose MMA latency and store/fence tails hide
-// under each other's sines.
-template <int F, int CH>
-struct EvalCfg {
-  static constexpr int CWG = F / 16 / CH;            // column groups = epilogue warps per TMEM lane quadrant
-  static constexpr int NT = 128 * CWG;               // epilogue threads
-  static constexpr int THREADS = NT + 32;            // + one warp that only issues MMAs
-  static constexpr int REGS = CH == 1 ? 56 : CH == 2 ? 72 : 96;  // register budget per thread the bound leaves
-  static constexpr int MIN_BLOCKS = 65536 / (THREADS * REGS) < 1 ? 1 : 65536 / (THREADS * REGS) > 8 ? 8 : 65536 / (THREADS * REGS);
-};
+// One CTA runs G GROUPS of 4 warps (128 threads: thread = one sample row = one TMEM lane) plus one MMA-issue warp.
+// Every group owns TWO tile slots and alternates between them, so 2G tiles (up to 8) are in flight per CTA and share
+// ONE staged copy of the weights:
+//
+//     coords -> A0 row -> [MMA layer 0] -> sin -> [MMA hidden 1] -> sin -> ... -> [MMA last (N = 16)] -> y -> store
+//
+// While a group computes the sines of one slot, the MMA of its other slot executes; MMA latency, TMEM loads, fences and
+// stores of one tile always sit under another tile's sines, which leaves the special-function unit (16 sin/clk/SM) as
+// the binding pipe.  ALL layers run on the tensor core: layer 0 as one K = 16 MMA against the hi/lo-split coordinate
+// row (fp32-grade), the last layer as N = 16 MMAs against hi/lo-split Wlast (brief_image.cuh); the bias of every layer
+// rides inside the MMA, so an epilogue element is FMUL.RZ + MUFU.SIN + half a pack.  There is no CTA-wide or
+// group-wide barrier in the tile loop: a warp only ever touches its own 32 rows, and the MMA warp serves the
+// (slot, group) units in a fixed order, blocking on each unit's "operand rows written" mbarrier (4 warp arrivals).
+constexpr int kEvalMaxGroups = 4;  // 4 groups x 2 slots x F columns <= 512 TMEM columns at F = 64
+constexpr int kEvalSlots = 2;
+constexpr int kEvalMaxUnits = kEvalMaxGroups * kEvalSlots;
+__host__ __device__ constexpr size_t eval_unit_bytes(int F) { return (size_t)kTile * F * 2 + (size_t)kTile * 16 * 2; }
 
-template <int F, int CH, bool DUMP>
-__global__ void __launch_bounds__(EvalCfg<F, CH>::THREADS, EvalCfg<F, CH>::MIN_BLOCKS) tc_eval_kernel(EvalArgs a) {
-  constexpr int CWG = EvalCfg<F, CH>::CWG;
-  constexpr int NT = EvalCfg<F, CH>::NT;  // epilogue threads; warp NW only issues MMAs (see the fit kernel)
-  constexpr int NW = NT / 32;
+template <int F, bool DUMP>
+__global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc_eval_kernel(EvalArgs a) {
+  constexpr int NC = F / 16;  // 16-column chunks per row
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_r;
+  __shared__ __align__(8) uint64_t bar_w, bar_mma[kEvalMaxUnits], bar_r[kEvalMaxUnits];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float4 s_row[kTile];
-  __shared__ float s_y[CWG][kTile];
-  __shared__ __align__(16) unsigned short s_out[kTile];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool mma_warp = warp == NW;
-  const int q = warp & 3, cg = mma_warp ? 0 : (warp >> 2), r = 32 * q + lane;
-  const int c_base = cg * CH;  // first 16-column chunk of this thread
+  const int G = (blockDim.x - 32) >> 7, U = G * kEvalSlots;
+  const bool mma_warp = warp == 4 * G;
+  const int g = warp >> 2, q = warp & 3, r = 32 * q + lane;
   int net_id;
   long long chunk;
   if (a.single_net >= 0) {
@@ -205,193 +205,190 @@ __global__ void __launch_bounds__(EvalCfg<F, CH>::THREADS, EvalCfg<F, CH>::MIN_B
   tc_load_net(sn, a.nets[net_id]);
   if (t == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_mma, 1);
-    mbar_init(&bar_r, NW);  // "the operand rows of this layer are written": one arrival per epilogue warp
+    for (int i = 0; i < U; ++i) {
+      mbar_init(&bar_mma[i], 1);
+      mbar_init(&bar_r[i], 4);  // "this unit's operand rows are written": one arrival per warp of the group
+    }
     fence_mbar_init();
   }
-  constexpr int TCOLS = tmem_cols_pow2(F);
-  if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
+  const uint32_t tcols = (uint32_t)tmem_cols_pow2(U * F);
+  if (warp == 0) tmem_alloc(&tmem_base_s, tcols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const NetDev& n = sn;
   const int NH = n.L - 2;
-  unsigned char* sW = smem;                                             // packed image (hidden weights + side)
-  const float* side = reinterpret_cast<const float*>(sW + img_side_off(F, NH));
-  const float4* s_w0b = reinterpret_cast<const float4*>(side);          // [F]
-  const float* s_wb = side + 4 * F;                                     // [NH][F]
-  const float* s_wl = s_wb + NH * F;                                    // [F]
-  const float* s_bl = s_wl + F;                                         // [4]
-  unsigned char* sAct = sW + img_bytes_padded(F, NH);                   // [128 x F] fp16 interleaved
+  unsigned char* sW = smem;  // packed image
+  unsigned char* sUnits = sW + img_bytes_padded(F, NH);  // per unit: [128 x F] activations | [128 x 16] layer-0 rows
   if (t == 0) {
     const uint32_t bytes = (uint32_t)img_bytes(F, NH);
     mbar_expect_tx(&bar_w, bytes);
     bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
   }
   const uint32_t tm = tmem_base_s;
-  const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * c_base;
-  const uint32_t aAct = smem_u32(sAct), aW = smem_u32(sW);
   const long long total = a.coords ? a.n_coords : n.n_vox;
   const long long n_tiles = (total + kTile - 1) / kTile;
-  const long long tile_begin = chunk * kEvalTilesPerBlock;
-  const long long tile_end = min(n_tiles, tile_begin + kEvalTilesPerBlock);
-  const float wh = n.wh;
-
-  auto load_row = [&](long long tile) {  // column group 0 fetches the tile's coordinates for everyone
-    const long long s = tile * kTile + r;
-    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-    if (tile < tile_end && s < total) {
-      if (a.coords) {
-        x0 = a.coords[s * n.in_dim];
-        x1 = a.coords[s * n.in_dim + 1];
-        x2 = n.in_dim == 3 ? a.coords[s * n.in_dim + 2] : 0.f;
-      } else {
-        brief_coords(n, a.axes, s, x0, x1, x2);
-      }
-    }
-    s_row[r] = make_float4(x0, x1, x2, 0.f);
-  };
-  auto signal = [&]() {  // epilogue warp -> MMA warp
-    tc_fence_before();
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_r);
-  };
-  if (!mma_warp && cg == 0) load_row(tile_begin);
+  const long long tile_begin = chunk * a.tiles_per_block;
+  const int count = (int)(min(n_tiles, tile_begin + a.tiles_per_block) - tile_begin);  // tiles of this CTA
+  const int rounds = (count + U - 1) / U;  // unit u serves tiles tile_begin + u, + U, ...
   mbar_wait(&bar_w, 0);
   __syncthreads();
 
   if (mma_warp) {
-    uint32_t ph_r = 0;
-    for (long long tile = tile_begin; tile < tile_end; ++tile)
-      for (int l = 1; l <= NH; ++l) {
-        TT(m0);
-        mbar_wait(&bar_r, ph_r);
-        ph_r ^= 1;
-        tc_fence_after();
-        TT(m1);
-        if (elect_one()) {
-          issue_forward<F>(tm, aAct, aW + (uint32_t)(l - 1) * F * F * 2);
-          commit(&bar_mma);
-        }
-        __syncwarp();
-        TT(m2);
-        TACC(0, m1 - m0); TACC(1, m2 - m1); TACC(7, 1);
+    const uint32_t aW = smem_u32(sW), aU0 = smem_u32(sUnits);
+    const int steps = NH + 2;  // MMA batches per tile
+    uint32_t ph = 0;           // every active unit's barrier flips once per step: one shared parity
+    constexpr uint32_t idesc_last = make_idesc(128, 16, false, false);
+    constexpr uint32_t idesc_f = make_idesc(128, F, false, false);
+    for (int it = 0; it < rounds; ++it)
+      for (int st = 0; st < steps; ++st) {
+        for (int slot = 0; slot < kEvalSlots; ++slot)
+          for (int gi = 0; gi < G; ++gi) {
+            const int u = gi * kEvalSlots + slot;
+            if (it * U + u >= count) continue;  // this unit has no tile in the last round
+            mbar_wait(&bar_r[u], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t act = aU0 + (uint32_t)u * (uint32_t)eval_unit_bytes(F);
+              const uint32_t d = tm + (uint32_t)u * F;
+              if (st == 0) {  // theta_0 = A0 [128 x 16] * B0^T
+                mma_f16(d, make_desc(act + kTile * F * 2, kActLBO, 128),
+                        make_desc(aW + (uint32_t)img_l0_off(F, NH), (F / 8) * 128, 128), idesc_f, 0);
+              } else if (st <= NH) {
+                issue_forward<F>(d, act, aW + (uint32_t)(st - 1) * F * F * 2);
+              } else {  // y = a_NH * [hi(Wlast); lo(Wlast)]^T  (N = 16)
+#pragma unroll
+                for (int k = 0; k < F / 16; ++k)
+                  mma_f16(d, make_desc(act + k * 2 * kActLBO, kActLBO, 128),
+                          make_desc(aW + (uint32_t)img_last_off(F, NH) + k * 2 * 256, 256, 128), idesc_last, k > 0);
+              }
+              commit(&bar_mma[u]);
+            }
+            __syncwarp();
+          }
+        ph ^= 1;
       }
   } else {
-    uint32_t phase = 0;
-    for (long long tile = tile_begin; tile < tile_end; ++tile) {
-      const long long s = tile * kTile + r;
-      const bool valid = s < total;
-      TT(e0);
-      const float4 xr = s_row[r];
-      // ---- layer 0 on CUDA cores -> fp16 operand rows (this thread: features 16 c_base .. 16 (c_base + CH) - 1)
+    const float inv_w0 = 1.0f / n.w0, inv_wh = 1.0f / n.wh;
+    uint32_t phase = 0;  // both slots wait the same number of times per round
+    for (int it = 0; it < rounds; ++it) {
+      const int u0 = g * kEvalSlots;
+      bool act[kEvalSlots], valid[kEvalSlots];
+      long long sidx[kEvalSlots];
 #pragma unroll
-      for (int h = 0; h < 2 * CH; ++h) {
-        float z[8];
-        const uint4 pk = first_layer8<DUMP>(s_w0b, 16 * c_base + 8 * h, xr.x, xr.y, xr.z, n.w0, z);
-        if (DUMP && valid)
-          for (int i = 0; i < 8; ++i)
-            if (16 * c_base + 8 * h + i < n.f) a.layers_out[s * n.f + 16 * c_base + 8 * h + i] = z[i];
-        *reinterpret_cast<uint4*>(sAct + chunk_off(r, 2 * c_base + h, kTile)) = pk;
+      for (int slot = 0; slot < kEvalSlots; ++slot) {
+        const int u = u0 + slot;
+        act[slot] = it * U + u < count;
+        sidx[slot] = (tile_begin + (long long)it * U + u) * kTile + r;
+        valid[slot] = act[slot] && sidx[slot] < total;
       }
-      TT(e1);
-      signal();
-      TT(e2);
-      TACC(0, e1 - e0); TACC(1, e2 - e1);
-      float ypart = 0.f;
-      // ---- hidden layers on the tensor core
-      for (int l = 1; l <= NH; ++l) {
-        TT(e3);
-        mbar_wait(&bar_mma, phase);
-        phase ^= 1;
-        tc_fence_after();
-        TT(e4);
-        float v[CH][16];
+      auto signal = [&](int u) {  // this warp's operand rows are written and its TMEM reads are done
+        tc_fence_before();
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_r[u]);
+      };
+      // ---- coordinates -> layer-0 operand row [x_hi(3) 1 x_lo(3) 1 | x_hi(3) 0 0 0 0 0]
 #pragma unroll
-        for (int c = 0; c < CH; ++c) tmem_ld16(my_tmem + 16 * c, v[c]);
-        tmem_ld_wait();
-        TT(e5);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const float* th = v[c];  // the packed weights carry omega and the bias: the accumulator IS the sine argument
-          if (DUMP && valid) {
-            float* zdump = a.layers_out + (long long)l * total * n.f + s * n.f;
-            for (int i = 0; i < 16; ++i)
-              if (16 * (c_base + c) + i < n.f) zdump[16 * (c_base + c) + i] = th[i] / wh;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[c][i] = fast_sin(v[c][i]);
-          if (l < NH) {
-            store_chunk16(sAct, r, c_base + c, v[c]);
+      for (int slot = 0; slot < kEvalSlots; ++slot) {
+        if (!act[slot]) continue;
+        const int u = u0 + slot;
+        unsigned char* sX0 = sUnits + (size_t)u * eval_unit_bytes(F) + (size_t)kTile * F * 2;
+        const long long s = sidx[slot];
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+        if (valid[slot]) {
+          if (a.coords) {
+            x0 = a.coords[s * n.in_dim];
+            x1 = a.coords[s * n.in_dim + 1];
+            x2 = n.in_dim == 3 ? a.coords[s * n.in_dim + 2] : 0.f;
           } else {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
-              ypart = fmaf(w4.x, v[c][i], ypart); ypart = fmaf(w4.y, v[c][i + 1], ypart);
-              ypart = fmaf(w4.z, v[c][i + 2], ypart); ypart = fmaf(w4.w, v[c][i + 3], ypart);
-            }
+            brief_coords(n, a.axes, s, x0, x1, x2);
           }
         }
-        TT(e6);
-        if (l < NH) signal();
-        TT(e7);
-        TACC(2, e4 - e3); TACC(3, e5 - e4); TACC(4, e6 - e5); TACC(5, e7 - e6);
+        const float h0 = __half2float(__float2half_rn(x0)), h1 = __half2float(__float2half_rn(x1)),
+                    h2 = __half2float(__float2half_rn(x2));
+        const uint32_t p01 = pack_f16x2(h0, h1), p21 = pack_f16x2(h2, 1.0f);
+        *reinterpret_cast<uint4*>(sX0 + chunk_off(r, 0, kTile)) =
+            make_uint4(p01, p21, pack_f16x2(x0 - h0, x1 - h1), pack_f16x2(x2 - h2, 1.0f));
+        *reinterpret_cast<uint4*>(sX0 + chunk_off(r, 1, kTile)) = make_uint4(p01, pack_f16x2(h2, 0.f), 0u, 0u);
+        signal(u);
       }
-      TT(e8);
-      // ---- last layer: fixed-order sum of the column groups' partial dot products, then the output epilogue
-      const bool full = tile * kTile + kTile <= total;
-      float y = ypart;
-      if (CWG > 1) {
-        s_y[cg][r] = ypart;
-        named_bar_sync(1, NT);
-      }
-      if (cg == 0) {
-        if (CWG > 1) {
-          y = 0.f;
+      // ---- sine layers: stage st reads theta_st from TMEM and writes a_st as the next MMA's operand
+      for (int st = 0; st <= NH; ++st) {
 #pragma unroll
-          for (int c = 0; c < CWG; ++c) y += s_y[c][r];
+        for (int slot = 0; slot < kEvalSlots; ++slot) {
+          if (!act[slot]) continue;
+          const int u = u0 + slot;
+          unsigned char* sAct = sUnits + (size_t)u * eval_unit_bytes(F);
+          const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + (uint32_t)u * F;
+          mbar_wait(&bar_mma[u], phase);
+          tc_fence_after();
+          float v[2][16];
+          tmem_ld16(my_tmem, v[0]);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NC) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);  // next chunk in flight under these sines
+            float* vc = v[c & 1];
+            if (DUMP && valid[slot]) {
+              float* zdump = a.layers_out + (long long)st * total * n.f + sidx[slot] * n.f;
+              const float inv = st == 0 ? inv_w0 : inv_wh;
+              for (int i = 0; i < 16; ++i)
+                if (16 * c + i < n.f) zdump[16 * c + i] = vc[i] * inv;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
+            store_chunk16(sAct, r, c, vc);
+          }
+          signal(u);
         }
-        y += s_bl[0];
+        phase ^= 1;
+      }
+      // ---- last layer: y = acc[0] + acc[1] (hi + lo rows of Wlast, bias inside), output epilogue
+#pragma unroll
+      for (int slot = 0; slot < kEvalSlots; ++slot) {
+        if (!act[slot]) continue;
+        const int u = u0 + slot;
+        const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + (uint32_t)u * F;
+        mbar_wait(&bar_mma[u], phase);
+        tc_fence_after();
+        uint32_t y0, y1;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(y0), "=r"(y1) : "r"(my_tmem) : "memory");
+        tmem_ld_wait();
+        const float y = __uint_as_float(y0) + __uint_as_float(y1);
+        const long long s = sidx[slot];
+        const bool full = (s - r) + kTile <= total;
         if (a.out_f32) {
-          if (valid) a.out_f32[s] = y;
+          if (valid[slot]) a.out_f32[s] = y;
         } else {
           void* dst = a.out_ptrs[net_id];
           if (a.out_dtype == 2) {
-            if (valid) reinterpret_cast<float*>(dst)[s] = y;
+            if (valid[slot]) reinterpret_cast<float*>(dst)[s] = y;
           } else {  // inverse normalisation + truncating cast
             const float vden = brief_denorm(n, y);
             if (a.out_dtype == 1) {
-              if (full) s_out[r] = (unsigned short)(int)vden;
-              else if (valid) reinterpret_cast<unsigned short*>(dst)[s] = (unsigned short)(int)vden;
-            } else {
-              if (full) reinterpret_cast<unsigned char*>(s_out)[r] = (unsigned char)(int)vden;
-              else if (valid) reinterpret_cast<unsigned char*>(dst)[s] = (unsigned char)(int)vden;
+              const uint32_t uv = (uint32_t)(unsigned short)(int)vden;
+              if (full) {  // 8 voxels per 16-byte store: lanes 0, 8, 16, 24 write the warp's 64 contiguous bytes
+                const uint32_t w = uv | (__shfl_down_sync(0xffffffffu, uv, 1) << 16);
+                const uint32_t w1 = __shfl_down_sync(0xffffffffu, w, 2), w2 = __shfl_down_sync(0xffffffffu, w, 4),
+                               w3 = __shfl_down_sync(0xffffffffu, w, 6);
+                if ((lane & 7) == 0)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dst) + s) = make_uint4(w, w1, w2, w3);
+              } else if (valid[slot]) {
+                reinterpret_cast<unsigned short*>(dst)[s] = (unsigned short)uv;
+              }
+            } else if (valid[slot]) {
+              reinterpret_cast<unsigned char*>(dst)[s] = (unsigned char)(int)vden;
             }
           }
         }
-        load_row(tile + 1);
       }
-      named_bar_sync(1, NT);
-      // staged tile -> 16-byte vector stores (256 B contiguous for uint16)
-      if (!a.out_f32 && a.out_dtype != 2 && full) {
-        void* dst = a.out_ptrs[net_id];
-        if (a.out_dtype == 1) {
-          if (t < 16)
-            reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(dst) + tile * kTile)[t] =
-                reinterpret_cast<const uint4*>(s_out)[t];
-        } else if (t < 8) {
-          reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(dst) + tile * kTile)[t] =
-              reinterpret_cast<const uint4*>(s_out)[t];
-        }
-      }
-      TT(e9);
-      TACC(6, e9 - e8); TACC(7, e9 - e0); TACC(8, 1);
+      phase ^= 1;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, TCOLS);
+  if (warp == 0) tmem_dealloc(tm, tcols);
 }
 
 // ==================================================================================================================
@@ -850,7 +847,19 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
 int tc_fpad(int f) { return ((f + 2 + 15) / 16) * 16; }  // two constant-one columns (bias hi / lo)
 
 size_t tc_wpack_bytes(int F, int L) { return img_bytes(F, L - 2); }
-size_t tc_eval_smem(int F, int L) { return img_bytes_padded(F, L - 2) + (size_t)kTile * F * 2; }
+// groups per CTA (two tile slots each): TMEM columns (2 G F <= 512) and shared memory (image + 2 G unit buffers)
+int tc_eval_groups(int F, int L) {
+  const size_t img = img_bytes_padded(F, L - 2);
+  const size_t budget = (F <= 32 ? (size_t)110 : (size_t)224) * 1024;  // F <= 32: two CTAs per SM
+  if (img + kEvalSlots * eval_unit_bytes(F) > budget) return 0;
+  int g = (int)((budget - img) / (kEvalSlots * eval_unit_bytes(F)));
+  g = g < kEvalMaxGroups ? g : kEvalMaxGroups;
+  g = g < 512 / (kEvalSlots * F) ? g : 512 / (kEvalSlots * F);
+  return g;
+}
+size_t tc_eval_smem(int F, int L) {
+  return img_bytes_padded(F, L - 2) + (size_t)tc_eval_groups(F, L) * kEvalSlots * eval_unit_bytes(F);
+}
 size_t tc_fit_smem(int F, int L) {  // sDz[2] + ring[NS + 2] + sX[2] + sDY + image
   return (size_t)(2 + (L - 1) + 2) * kTile * F * 2 + 3 * (size_t)kTile * 16 * 2 + img_bytes_padded(F, L - 2);
 }
@@ -872,44 +881,34 @@ bool tc_supported(int f, int L, int in_dim, int out_dim) {
   if (L < 3 || F > 64) return false;
   if (3 * F + fit_acc_blocks(L - 2) * F > 512) return false;  // TMEM: Zf, Zb, Xb + packed dW accumulators
   if (tc_fit_smem(F, L) > 221 * 1024) return false;           // + ~5 KB static shared memory <= 227 KB
+  if (tc_eval_groups(F, L) < 1) return false;
   return true;
 }
 
-template <int F, int CH>
-static cudaError_t launch_eval_fc(const EvalArgs& a, int L_max, int n_blocks, cudaStream_t st) {
+template <int F>
+static cudaError_t launch_eval_f(const EvalArgs& a, int L_max, int n_blocks, cudaStream_t st) {
+  const int G = tc_eval_groups(F, L_max);
+  if (G < 1) return cudaErrorInvalidValue;
   const size_t smem = tc_eval_smem(F, L_max);
   cudaError_t e;
   if (a.layers_out) {
-    e = cudaFuncSetAttribute(tc_eval_kernel<F, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(tc_eval_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, CH, true><<<n_blocks, EvalCfg<F, CH>::THREADS, smem, st>>>(a);
+    tc_eval_kernel<F, true><<<n_blocks, G * 128 + 32, smem, st>>>(a);
   } else {
-    e = cudaFuncSetAttribute(tc_eval_kernel<F, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(tc_eval_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, CH, false><<<n_blocks, EvalCfg<F, CH>::THREADS, smem, st>>>(a);
+    tc_eval_kernel<F, false><<<n_blocks, G * 128 + 32, smem, st>>>(a);
   }
   return cudaGetLastError();
 }
 
-// chunks per thread: default per width, BRIEF_EVAL_CH overrides (tuning)
-static int eval_ch(int F) {
-  static const int env = [] { const char* e = getenv("BRIEF_EVAL_CH"); return e ? atoi(e) : 0; }();
-  const int n = F / 16;
-  if (env > 0 && n % env == 0) return env;
-  return F == 64 ? 2 : F == 48 ? 3 : F == 32 ? 2 : 1;
-}
-
 cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st) {
-  const int ch = eval_ch(F_PAD);
-  switch (F_PAD * 8 + ch) {
-    case 16 * 8 + 1: return launch_eval_fc<16, 1>(a, L_max, n_blocks, st);
-    case 32 * 8 + 1: return launch_eval_fc<32, 1>(a, L_max, n_blocks, st);
-    case 32 * 8 + 2: return launch_eval_fc<32, 2>(a, L_max, n_blocks, st);
-    case 48 * 8 + 1: return launch_eval_fc<48, 1>(a, L_max, n_blocks, st);
-    case 48 * 8 + 3: return launch_eval_fc<48, 3>(a, L_max, n_blocks, st);
-    case 64 * 8 + 1: return launch_eval_fc<64, 1>(a, L_max, n_blocks, st);
-    case 64 * 8 + 2: return launch_eval_fc<64, 2>(a, L_max, n_blocks, st);
-    case 64 * 8 + 4: return launch_eval_fc<64, 4>(a, L_max, n_blocks, st);
+  switch (F_PAD) {
+    case 16: return launch_eval_f<16>(a, L_max, n_blocks, st);
+    case 32: return launch_eval_f<32>(a, L_max, n_blocks, st);
+    case 48: return launch_eval_f<48>(a, L_max, n_blocks, st);
+    case 64: return launch_eval_f<64>(a, L_max, n_blocks, st);
     default: return cudaErrorInvalidValue;
   }
 }
