@@ -47,8 +47,8 @@ using namespace umma;
 #ifdef BRIEF_TC_TIMING
 __device__ unsigned long long g_tc_timing[64];
 #define TT(var) const long long var = clock64()
-#define TACC(slot, expr) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp >= NW)) \
-    atomicAdd(&g_tc_timing[(slot) + (warp == 0 ? 0 : warp == NW ? 16 : 32)], (unsigned long long)(expr)); } while (0)
+#define TACC(slot, expr) do { if (blockIdx.x == 0 && lane == 0 && tslot >= 0) \
+    atomicAdd(&g_tc_timing[tslot + (slot)], (unsigned long long)(expr)); } while (0)
 #else
 #define TT(var)
 #define TACC(slot, expr)
@@ -394,47 +394,77 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
 // ==================================================================================================================
 // fit: gather + forward + weighted L2 + backward -> per-slice gradient partials
 // ==================================================================================================================
-// TWO tiles are in flight per CTA, in opposite phases: while tile A walks backward through the layers, tile B (the
-// next 128 samples) walks forward.  The same 128*(F/16) threads alternate between them, so every tensor-core phase
-// (MMA issue + execution + commit latency, ~450-750 cycles, measured) runs underneath the other tile's epilogue:
+// TWO tiles are in flight per CTA, in opposite phases, and each has its OWN warps: group B walks tile k+1 FORWARD
+// (layer-0 operand row, sines, last layer, loss, dz_NH) while group A walks tile k BACKWARD (dz_{l-1} = dX * cos).
+// The two chains only meet in the tensor pipe: a dedicated MMA-issue warp polls both groups' "operands written"
+// mbarriers and issues whichever batch is ready (backward first: it is the longer chain), so one tile's MMA latency,
+// TMEM loads, fences and stores sit under the other tile's special-function work instead of being serialised in one
+// thread (a tcgen05.mma blocks its issuing thread for about as long as it executes: ~62 cycles per 128x64x16,
+// tests/cuda/umma_timing_probe.cu).  A fourth role, the sampler warp, stages the next tile's samples.
 //
-//     wait A  ->  epilogue A (dz_{l-1})  ->  signal  ->  wait B  ->  epilogue B (a_j)  ->  signal  -> ...
+// Every sine layer's argument comes out of an MMA (bias and omega inside, brief_image.cuh): layer 0 is one K = 16 MMA
+// against the hi/lo-split coordinate row, which doubles as the B operand of the dW0 contraction.
 //
-// A tcgen05.mma blocks the issuing thread for about as long as it executes (measured: ~62 cycles per 128x64x16
-// instruction, tests/cuda/umma_timing_probe.cu), so MMAs are issued by a DEDICATED extra warp that mirrors the
-// schedule and is told through mbarriers (one arrival per epilogue warp) when a tile's operands are in place;
-// the epilogue warps never wait for an issue, only for the commit of the MMAs they consume.
-//
-// Both tiles' activations fit because their lifetimes are complementary: backward stage l of A still needs
-// a_0..a_{l-1} while forward stage j = NH+1-l of B has produced a_0..a_j.  Even tiles keep layer j in ring slot j,
-// odd tiles in slot R-1-j (R = NS + 2 slots), so a forward write only ever lands in a slot the backward tile has
-// finished with (the wait on A's barrier that precedes B's epilogue also covers A's trailing dW MMAs).
+// Both tiles' activations fit because their lifetimes are complementary: backward stage l of tile k still needs
+// a_0..a_{l-1} while the forward pass of tile k+1 has produced a_0..a_j.  Even tiles keep layer j in ring slot j, odd
+// tiles in slot R-1-j (R = NS + 2 slots); the MMA warp issues forward batch b of tile k+1 only after backward batch
+// b-2 of tile k (whose trailing dW is the last reader of the slot that a_b overwrites) — the pipe executes in order.
+// Hand-overs between the groups go through tcgen05.commit mbarriers: bar_f1 (tile k's dW_1 done: the dz buffer that
+// tile k+1's dz_NH goes to is free) and bar_f2 (tile k complete: its ring slots and coordinate rows are free).
 //
 // shared memory (dynamic):  sDz[2] | ring[R] | sX[2] | sDY | image          (NS = L-1 sine layers, R = NS + 2)
 //   sDz first: the M = 64 dW contractions read 8 feature groups (16 KB) from the start of a buffer whatever F is.
-// TMEM columns: Zf [0,F) forward z | Zb [F,2F) recomputed z | Xb [2F,3F) dX | accumulators from 3F:
+// TMEM columns: Zf [0,F) forward theta | Zb [F,2F) recomputed theta | Xb [2F,3F) dX | accumulators from 3F:
 //   accumulator i (M = 64: 16 lanes per quadrant) lives in column block i/2, lane half i%2 — two per block.
 //   i = 0..NH-1: dW_{i+1} (F columns; column f = db), i = NH: dW0 block (16 columns), i = NH+1: dWlast block.
+// Optional: Zb double-buffered (when the columns allow it) so that the recomputed theta of the NEXT backward stage is
+// issued behind the current stage's dW instead of in front of its dX.  Measured neutral on B200 (178 vs 174 us at
+// F = 64): the tensor pipe is operand-bandwidth-bound here (~100 B/clk of shared-memory operand fetch), so moving four
+// MMAs off the critical path does not shorten it.  Kept switchable for wider tiles.
+constexpr bool kFitPrefetchTheta = false;
 __host__ __device__ constexpr int fit_acc_blocks(int NH) { return (NH + 2 + 1) / 2; }
-__host__ __device__ constexpr int fit_tmem_cols(int F, int NH) { return tmem_cols_pow2(3 * F + fit_acc_blocks(NH) * F); }
+__host__ __device__ constexpr bool fit_zb_double(int F, int NH) {
+  return kFitPrefetchTheta && 4 * F + fit_acc_blocks(NH) * F <= 512;
+}
+__host__ __device__ constexpr int fit_fixed_cols(int F, int NH) { return fit_zb_double(F, NH) ? 4 * F : 3 * F; }
+__host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
+  return tmem_cols_pow2(fit_fixed_cols(F, NH) + fit_acc_blocks(NH) * F);
+}
 
 template <int F>
-__global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
-  constexpr int CW = TcCfg<F>::CW;
-  constexpr int NT = TcCfg<F>::THREADS;   // epilogue threads; warp NW is the MMA warp, warp NW+1 the sampler warp
-  constexpr int NW = NT / 32;
+struct FitCfg {
+  static constexpr int NC = F / 16;                       // 16-column chunks per row
+  static constexpr int CPT = (F == 64 || F == 32) ? 2 : 1;  // chunks per thread
+  static constexpr int CG = NC / CPT;                     // column groups per role
+  static constexpr int GW = 4 * CG;                       // warps per role (A or B)
+  static constexpr int GT = GW * 32;                      // threads per role
+  static constexpr int THREADS = 2 * GT + 64;             // + MMA-issue warp + sampler warp
+  static constexpr int MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 3;  // must match tc_fit_ctas_per_sm()
+};
+
+template <int F>
+__global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
+  using C = FitCfg<F>;
+  constexpr int CPT = C::CPT, CG = C::CG, GW = C::GW, GT = C::GT, NC = C::NC;
+  constexpr int NW = 2 * GW;  // epilogue warps: [0, GW) group B (forward), [GW, 2 GW) group A (backward)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_gfull[2], bar_gfree[2];
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_lb, bar_f1, bar_f2, bar_gfull[2], bar_gfree[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float4 s_g[2][kTile];  // sampler staging: (x0, x1, x2, normalised target) per row
   __shared__ float s_gw[2][kTile];                //                  loss weight per row
-  __shared__ float s_y[CW][kTile];
+  __shared__ float s_y[CG][kTile];
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const bool mma_warp = warp == NW, sampler_warp = warp == NW + 1;
-  const int q = warp & 3, cg = warp >= NW ? CW : (warp >> 2), r = 32 * q + lane;
+  const bool group_a = warp >= GW && warp < NW;
+  const int gw = group_a ? warp - GW : warp;  // warp index inside the role
+  const int q = warp & 3, cg = (gw >> 2) % CG, r = 32 * q + lane;
+  const int c_base = cg * CPT;                // first 16-column chunk of this thread
+#ifdef BRIEF_TC_TIMING
+  const int tslot = warp == 0 ? 0 : warp == GW ? 16 : warp == NW ? 32 : warp == NW + 1 ? 48 : -1;
+#endif
   const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
   const int net_id = a.work_net[wi];
   const int slice = blockIdx.x - a.work_prefix[wi];
@@ -443,11 +473,16 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
     mbar_init(&bar_w, 1);
     mbar_init(&bar_a, 1);
     mbar_init(&bar_b, 1);
-    mbar_init(&bar_ra, NW);  // "operands of the backward tile are in place": one arrival per epilogue warp
-    mbar_init(&bar_rb, NW);  // same for the forward tile
+    mbar_init(&bar_f1, 1);
+    mbar_init(&bar_f2, 1);
+    mbar_init(&bar_ra, GW);  // "operands of the backward tile are in place": one arrival per warp of group A
+    mbar_init(&bar_rb, GW);  // same for the forward tile / group B
+    // "loss phase done" has its own barrier: group B raises it and the NEXT tile's first bar_rb signal back to back,
+    // and a parity wait cannot tell a phase from the one two completions later
+    mbar_init(&bar_lb, GW);
     for (int k = 0; k < 2; ++k) {
       mbar_init(&bar_gfull[k], 1);    // sampler warp: staging slot k holds a tile's samples
-      mbar_init(&bar_gfree[k], NW);   // epilogue warps: staging slot k has been consumed
+      mbar_init(&bar_gfree[k], GW);   // group B: staging slot k has been consumed
     }
     fence_mbar_init();
   }
@@ -467,56 +502,32 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   unsigned char* sDY = sX + 2 * BLK;
   unsigned char* sW = sDY + BLK;
   const float* side = reinterpret_cast<const float*>(sW + img_side_off(F, NH));
-  const float4* s_w0b = reinterpret_cast<const float4*>(side);
-  const float* s_wb = side + 4 * F;
-  const float* s_wl = s_wb + NH * F;
+  const float* s_wl = side + 4 * F + NH * F;
   const float* s_bl = s_wl + F;
   if (t == 0) {
     const uint32_t bytes = (uint32_t)img_bytes(F, NH);
     mbar_expect_tx(&bar_w, bytes);
     bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
   }
-  if (cg == 0) {  // second column group of the 16-column blocks is constant zero
-    *reinterpret_cast<uint4*>(sX + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(sX + BLK + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
+  if (!group_a && warp < GW && cg == 0)  // second column group of the dY block is constant zero
     *reinterpret_cast<uint4*>(sDY + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
-  }
 
   const uint32_t tm = tmem_base_s;
-  const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * cg;
-  const uint32_t TZF = tm, TZB = tm + F, TXB = tm + 2 * F;
-  auto acc_addr = [&](int i) { return tm + 3 * F + (uint32_t)(i >> 1) * F + ((uint32_t)(i & 1) << 20); };  // lane 16 = 16 << 16
+  const uint32_t my_tmem = tm + ((uint32_t)(32 * q) << 16) + 16 * c_base;
+  const bool zb2 = fit_zb_double(F, NH);           // theta of backward stage l lives in Zb[l & 1] (Zb[0] if single)
+  const uint32_t zb_stride = zb2 ? F : 0;
+  const uint32_t acc0 = (uint32_t)fit_fixed_cols(F, NH);
+  const uint32_t TZF = tm, TZB = tm + F, TXB = tm + 2 * F + zb_stride;
+  auto acc_addr = [&](int i) { return tm + acc0 + (uint32_t)(i >> 1) * F + ((uint32_t)(i & 1) << 20); };  // lane 16 = 16 << 16
   const uint32_t aDz = smem_u32(sDz), aRing = smem_u32(sRing), aX = smem_u32(sX), aDY = smem_u32(sDY), aW = smem_u32(sW);
   auto slot = [&](int parity, int j) { return (uint32_t)(parity ? R - 1 - j : j) * BUF; };  // byte offset into the ring
-  uint32_t ph_a = 0, ph_b = 0;
   const float wh = n.wh, w0 = n.w0;
   const long long s_begin = (long long)slice * n.slice_len;
   const long long s_end = min((long long)n.batch, s_begin + n.slice_len);
   const int n_tiles = (int)((s_end - s_begin + kTile - 1) / kTile);
+  const int sb_flip = (NH - 1) & 1;  // dz_NH of tile k+1 goes where dz_1 of tile k lived: start buffer sb(k+1) = sb(k) ^ sb_flip
   float loss_acc = 0.f;
 
-  // ---- the sampler (main.py:126-163 / whole-block cube) for one tile, run by the sampler warp one tile ahead of its
-  //      use: index -> coordinates (axis tables), raw voxel -> normalised target, loss weight; 4 rows per lane
-  auto sample_tile = [&](int tile, int slot_id) {
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const int row = lane + 32 * h;
-      const long long s = s_begin + (long long)tile * kTile + row;
-      float x0 = 0.f, x1 = 0.f, x2 = 0.f, yv = 0.f, wv = 0.f;
-      if (s < s_end) {
-        long long idx;
-        if (n.mode == 0) idx = s;
-        else if (a.idx) idx = a.idx[n.idx_off + s];
-        else idx = brief_sample_index(a.seed, a.step, (uint32_t)net_id, (uint64_t)s, (uint64_t)n.n_vox);
-        brief_coords(n, a.axes, idx, x0, x1, x2);
-        const float raw = brief_raw_value(n, idx);
-        yv = brief_normalize(n, raw);
-        wv = brief_weight(n, idx, raw);
-      }
-      s_g[slot_id][row] = make_float4(x0, x1, x2, yv);
-      s_gw[slot_id][row] = wv;
-    }
-  };
   // epilogue warp -> MMA warp: this warp's operand rows are written (and its TMEM reads are done)
   auto signal = [&](uint64_t* bar) {
     tc_fence_before();
@@ -524,266 +535,274 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
   };
-  auto epi_sync = [&]() { named_bar_sync(1, NT); };  // epilogue threads only
 
-  // ---- forward prologue of a tile: coordinates -> s_row / sX, layer 0 on CUDA cores -> a_0
-  float4 xf = make_float4(0.f, 0.f, 0.f, 0.f);  // coordinates of the forward tile's row, xb: of the backward tile's
-  float4 xb = xf;
-  auto fwd_prologue = [&](int tile) {
-    const int parity = tile & 1;
-    mbar_wait(&bar_gfull[parity], (uint32_t)(tile >> 1) & 1);
-    xf = s_g[parity][r];
-    if (cg == 0) {
-      // B operand of the dW0 contraction: [x_hi(3), 1, x_lo(3), 0]  (hi/lo split keeps fp32-grade coordinates)
-      const float h0 = __half2float(__float2half_rn(xf.x)), h1 = __half2float(__float2half_rn(xf.y)),
-                  h2 = __half2float(__float2half_rn(xf.z));
-      *reinterpret_cast<uint4*>(sX + parity * BLK + chunk_off(r, 0, kTile)) =
-          make_uint4(pack_f16x2(h0, h1), pack_f16x2(h2, 1.0f), pack_f16x2(xf.x - h0, xf.y - h1), pack_f16x2(xf.z - h2, 0.f));
-    }
-    unsigned char* a0 = sRing + slot(parity, 0);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float z[8];
-      *reinterpret_cast<uint4*>(a0 + chunk_off(r, 2 * cg + h, kTile)) =
-          first_layer8<false>(s_w0b, 16 * cg + 8 * h, xf.x, xf.y, xf.z, w0, z);
-    }
-  };
-  // ---- forward stage j of a tile: z_j (in Zf) -> a_j ; at j == NH also the last layer's partial dot product
-  float th[16];      // sine arguments of the last hidden layer of the forward tile (dz_NH needs their cosines)
-  float ypart = 0.f;
-  auto issue_fwd = [&](int parity, int j) {  // elected thread
-    issue_forward<F>(TZF, aRing + slot(parity, j - 1), aW + (uint32_t)(j - 1) * F * F * 2);
-    commit(&bar_b);
-  };
-  auto fwd_epilogue = [&](int parity, int j) {
-    float v[16];
-    tmem_ld16(my_tmem, th);  // the packed weights carry omega and the bias: the accumulator IS the sine argument
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fast_sin(th[i]);
-    store_chunk16(sRing + slot(parity, j), r, cg, v);
-    if (j == NH) {
-      ypart = 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
-        ypart = fmaf(w4.x, v[i], ypart); ypart = fmaf(w4.y, v[i + 1], ypart);
-        ypart = fmaf(w4.z, v[i + 2], ypart); ypart = fmaf(w4.w, v[i + 3], ypart);
-      }
-    }
-  };
-  // ---- loss (datal2, main.py:176-182), scaled output gradient and dz_NH for the tile that just finished forward
-  auto loss_phase = [&](int tile) {
-    s_y[cg][r] = ypart;
-    epi_sync();
-    // every thread of the row forms y, the error and dy itself (same operands, same order: identical values), so one
-    // barrier is enough; column group 0 additionally accumulates the loss and writes the dWlast operand block
-    float y = s_bl[0];
-#pragma unroll
-    for (int c = 0; c < CW; ++c) y += s_y[c][r];
-    float dys = 0.f;
-    if (s_begin + (long long)tile * kTile + r < s_end) {
-      const float e = y - xf.w;  // xf.w: the row's normalised target
-      const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : s_gw[tile & 1][r];
-      if (cg == 0) loss_acc = fmaf(wt * e, e, loss_acc);
-      dys = kGradScale * wt * e;
-    }
-    if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
-    dys *= wh;
-    float dz[16];
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * cg + i);
-      dz[i] = dys * w4.x * fast_cos(th[i]); dz[i + 1] = dys * w4.y * fast_cos(th[i + 1]);
-      dz[i + 2] = dys * w4.z * fast_cos(th[i + 2]); dz[i + 3] = dys * w4.w * fast_cos(th[i + 3]);
-    }
-    store_chunk16_sat(sDz, r, cg, dz);
-    // staging slot consumed (coordinates and target live on in xf / xb); s_y may be rewritten only after the next
-    // tile's forward pass, i.e. after many barriers
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_gfree[tile & 1]);
-  };
-  // ---- backward stage l of a tile.  issue: what the epilogue waits for (z_{l-1} recomputed, dX_{l-1}) is committed
-  //      first; dW_l, db_l (+ dWlast at l == NH) follow and are tracked by the tile's next commit.
-  int cur = 0;
-  auto issue_bwd = [&](int parity, int l, bool accumulate) {  // elected thread
-    const uint32_t dzb = aDz + (uint32_t)cur * BUF;
-    if (l >= 2) issue_forward<F>(TZB, aRing + slot(parity, l - 2), aW + (uint32_t)(l - 2) * F * F * 2);
-    issue_dx<F>(TXB, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
-    commit(&bar_a);
-    issue_dw<F>(acc_addr(l - 1), dzb, aRing + slot(parity, l - 1), accumulate);
-    if (l == NH) issue_dw<16>(acc_addr(NH + 1), aRing + slot(parity, NH), aDY, accumulate);
-  };
-  auto bwd_epilogue = [&](int l) {  // dz_{l-1} = dX_{l-1} * w * cos(w z_{l-1})
-    float vx[16], dz[16];
-    if (l >= 2) {
-      float vz[16];
-      tmem_ld16(my_tmem + F, vz);
-      tmem_ld16(my_tmem + 2 * F, vx);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) dz[i] = vx[i] * fast_cos(vz[i]);  // vx = w * (dz_l W_l): omega-scaled weights
-    } else {  // layer 0: z_0 recomputed on CUDA cores from the backward tile's coordinates
-      const float w0_over_wh = w0 / wh;
-      tmem_ld16(my_tmem + 2 * F, vx);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float4 w = s_w0b[16 * cg + i];
-        float z = w.w;
-        z = fmaf(w.x, xb.x, z); z = fmaf(w.y, xb.y, z); z = fmaf(w.z, xb.z, z);
-        dz[i] = vx[i] * w0_over_wh * fast_cos(w0 * z);
-      }
-    }
-    store_chunk16_sat(sDz + (size_t)(cur ^ 1) * BUF, r, cg, dz);
-    cur ^= 1;
-  };
-
-  // ================================================ schedule ====================================================
   mbar_wait(&bar_w, 0);
   if (mma_warp) {
-    // ---- the MMA warp mirrors the epilogue warps' schedule; one elected lane issues
-    uint32_t ph_ra = 0, ph_rb = 0;
-    if (n_tiles > 0) {
-      for (int j = 1; j <= NH; ++j) {
-        mbar_wait(&bar_rb, ph_rb);
-        ph_rb ^= 1;
-        tc_fence_after();
-        if (elect_one()) issue_fwd(0, j);
-        __syncwarp();
-      }
-    }
+    // ============================================ MMA-issue warp ===============================================
+    // B events per tile, in order: NH+1 forward batches (0 = layer 0), then the "loss done" signal that arms the
+    // backward chain.  A batches per tile: NH gated ones (l = NH..1: recomputed theta_{l-1}, dX_{l-1} | commit |
+    // dW_l) and the final dW0.
+    constexpr uint32_t idesc_f = make_idesc(128, F, false, false);
+    uint32_t ph_ra = 0, ph_rb = 0, ph_lb = 0;
+    int kA = 0, ia = 0, kB = 0, ib = 0, loss_done = 0, sbA = 0;
+    auto layer0 = [&](uint32_t d, int parity) {  // theta_0 = A0 [128 x 16] * B0^T
+      mma_f16(d, make_desc(aX + parity * BLK, kActLBO, 128), make_desc(aW + (uint32_t)img_l0_off(F, NH), (F / 8) * 128, 128),
+              idesc_f, 0);
+    };
     TT(m_start);
-    for (int i = 0; i < n_tiles; ++i) {
-      const int pa = i & 1, pb = pa ^ 1;
-      const bool has_b = i + 1 < n_tiles;
+    while (kA < n_tiles) {
+      bool progressed = false;
       TT(m0);
-      mbar_wait(&bar_ra, ph_ra);  // dz_NH / sDY of tile i and a_0 / sX of tile i+1 are in place
-      ph_ra ^= 1;
-      tc_fence_after();
-      TT(m1);
-      if (elect_one()) {
-        issue_bwd(pa, NH, i > 0);
-        if (has_b) issue_fwd(pb, 1);
-      }
-      __syncwarp();
-      TT(m2);
-      TACC(0, m1 - m0); TACC(1, m2 - m1);
-      for (int j = 1; j <= NH; ++j) {
-        const int l = NH + 1 - j;
-        TT(m3);
-        mbar_wait(&bar_ra, ph_ra);  // dz_{l-1} written
+      // ---- backward chain of tile kA
+      bool a_ready = false;
+      if (ia == 0) {
+        a_ready = loss_done > kA;
+      } else if (mbar_test(&bar_ra, ph_ra)) {
         ph_ra ^= 1;
+        a_ready = true;
+      }
+      if (a_ready) {
         tc_fence_after();
-        TT(m4);
-        cur ^= 1;  // mirrors bwd_epilogue's buffer flip
+        const int pa = kA & 1;
+        const bool accum = kA > 0;
         if (elect_one()) {
-          if (l > 1) {
-            issue_bwd(pa, l - 1, i > 0);
-          } else {  // dW0 += dz_0^T [x_hi, 1, x_lo]; its commit also covers dW_1, so waiting on it frees the tile
-            issue_dw<16>(acc_addr(NH), aDz + (uint32_t)cur * BUF, aX + pa * BLK, i > 0);
+          if (ia < NH) {
+            const int l = NH - ia;
+            const uint32_t dzb = aDz + (uint32_t)(sbA ^ (ia & 1)) * BUF;  // dz_l
+            auto recompute = [&](int m) {  // theta_m -> Zb[(m + 1) & 1], read by backward stage m + 1
+              const uint32_t d = TZB + (uint32_t)((m + 1) & 1) * zb_stride;
+              if (m >= 1) issue_forward<F>(d, aRing + slot(pa, m - 1), aW + (uint32_t)(m - 1) * F * F * 2);
+              else layer0(d, pa);
+            };
+            if (!zb2 || l == NH) recompute(l - 1);
+            issue_dx<F>(TXB, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
             commit(&bar_a);
+            issue_dw<F>(acc_addr(l - 1), dzb, aRing + slot(pa, l - 1), accum);
+            if (l == NH) issue_dw<16>(acc_addr(NH + 1), aRing + slot(pa, NH), aDY, accum);
+            if (l == 1) commit(&bar_f1);  // dW_1 done: the buffer of dz_1 may take the next tile's dz_NH
+            if (zb2 && l >= 2) recompute(l - 2);  // next stage's theta, behind this stage's dW
+          } else {  // dW0 += dz_0^T [x_hi, 1, x_lo, ...]; completes the tile
+            issue_dw<16>(acc_addr(NH), aDz + (uint32_t)(sbA ^ (NH & 1)) * BUF, aX + pa * BLK, accum);
+            commit(&bar_f2);
           }
         }
         __syncwarp();
-        TT(m5);
-        TACC(2, m4 - m3); TACC(3, m5 - m4);
-        if (has_b && j < NH) {
-          mbar_wait(&bar_rb, ph_rb);  // a_j written
-          ph_rb ^= 1;
+        if (++ia > NH) { ia = 0; ++kA; sbA ^= sb_flip; }
+        progressed = true;
+        { TT(m1); TACC(0, m1 - m0); TACC(1, 1); }
+      }
+      TT(m2);
+      // ---- forward chain of tile kB (ring safety: batch b only after backward batch b-2 of tile kB-1 was issued)
+      if (kB < n_tiles) {
+        const bool allowed = ib > NH || ib < 2 || kA >= kB || (kA == kB - 1 && ia >= ib - 1);
+        if (allowed && (ib <= NH ? mbar_test(&bar_rb, ph_rb) : mbar_test(&bar_lb, ph_lb))) {
+          if (ib <= NH) ph_rb ^= 1; else ph_lb ^= 1;
           tc_fence_after();
-          TT(m6);
-          if (elect_one()) issue_fwd(pb, j + 1);
-          __syncwarp();
-          TT(m7);
-          TACC(4, m6 - m5); TACC(5, m7 - m6);
+          if (ib <= NH) {
+            if (elect_one()) {
+              const int pb = kB & 1;
+              if (ib == 0) layer0(TZF, pb);
+              else issue_forward<F>(TZF, aRing + slot(pb, ib - 1), aW + (uint32_t)(ib - 1) * F * F * 2);
+              commit(&bar_b);
+            }
+            __syncwarp();
+            ++ib;
+          } else {  // loss phase done: dz_NH, sDY in place
+            loss_done = kB + 1;
+            ib = 0;
+            ++kB;
+          }
+          progressed = true;
+          { TT(m3); TACC(2, m3 - m2); TACC(3, 1); }
         }
       }
-      cur = 0;
+      if (!progressed) __nanosleep(20);
+      if (!progressed) { TT(m4); TACC(4, m4 - m0); }
     }
-    { TT(m_end); TACC(6, m_end - m_start); TACC(7, n_tiles); }
+    { TT(m_end); TACC(5, m_end - m_start); TACC(6, n_tiles); }
   } else if (sampler_warp) {
-    // ---- the sampler warp runs up to two tiles ahead of the epilogue warps
+    // ============================================ sampler warp ==================================================
+    // main.py:126-163 / whole-block cube for one tile, up to two tiles ahead of its use: index -> coordinates (axis
+    // tables), raw voxel -> normalised target, loss weight; 4 rows per lane
     for (int k = 0; k < n_tiles; ++k) {
-      TT(g0);
-      if (k >= 2) mbar_wait(&bar_gfree[k & 1], (uint32_t)((k >> 1) - 1) & 1);
-      TT(g1);
-      sample_tile(k, k & 1);
+      const int sl = k & 1;
+      if (k >= 2) mbar_wait(&bar_gfree[sl], (uint32_t)((k >> 1) - 1) & 1);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int row = lane + 32 * h;
+        const long long s = s_begin + (long long)k * kTile + row;
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, yv = 0.f, wv = 0.f;
+        if (s < s_end) {
+          long long idx;
+          if (n.mode == 0) idx = s;
+          else if (a.idx) idx = a.idx[n.idx_off + s];
+          else idx = brief_sample_index(a.seed, a.step, (uint32_t)net_id, (uint64_t)s, (uint64_t)n.n_vox);
+          brief_coords(n, a.axes, idx, x0, x1, x2);
+          const float raw = brief_raw_value(n, idx);
+          yv = brief_normalize(n, raw);
+          wv = brief_weight(n, idx, raw);
+        }
+        s_g[sl][row] = make_float4(x0, x1, x2, yv);
+        s_gw[sl][row] = wv;
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_gfull[k & 1]);
-      TT(g2);
-      TACC(0, g1 - g0); TACC(1, g2 - g1); TACC(7, 1);
+      if (lane == 0) mbar_arrive(&bar_gfull[sl]);
     }
-  } else {
-    // ---- epilogue warps
-    if (n_tiles > 0) {
-      // tile 0 walks forward alone
-      fwd_prologue(0);
+  } else if (!group_a) {
+    // ============================================ group B: forward ==============================================
+    uint32_t ph_b = 0;
+    int sb = 0;
+    TT(b_start);
+    for (int k = 0; k < n_tiles; ++k) {
+      const int p = k & 1;
+      TT(b0);
+      if (k >= 2) mbar_wait(&bar_f2, (uint32_t)k & 1);  // tile k-2 complete: ring slots of this parity and sX[p] are free
+      TT(b1);
+      mbar_wait(&bar_gfull[p], (uint32_t)(k >> 1) & 1);
+      TT(b2);
+      TACC(0, b1 - b0); TACC(1, b2 - b1);
+      const float4 xf = s_g[p][r];
+      if (cg == 0) {  // layer-0 operand row [x_hi(3) 1 x_lo(3) 1 | x_hi(3) 0 0 0 0 0]; also the B operand of dW0
+        const float h0 = __half2float(__float2half_rn(xf.x)), h1 = __half2float(__float2half_rn(xf.y)),
+                    h2 = __half2float(__float2half_rn(xf.z));
+        const uint32_t p01 = pack_f16x2(h0, h1), p21 = pack_f16x2(h2, 1.0f);
+        *reinterpret_cast<uint4*>(sX + p * BLK + chunk_off(r, 0, kTile)) =
+            make_uint4(p01, p21, pack_f16x2(xf.x - h0, xf.y - h1), pack_f16x2(xf.z - h2, 1.0f));
+        *reinterpret_cast<uint4*>(sX + p * BLK + chunk_off(r, 1, kTile)) = make_uint4(p01, pack_f16x2(h2, 0.f), 0u, 0u);
+      }
       signal(&bar_rb);
-      for (int j = 1; j <= NH; ++j) {
+      float ypart = 0.f;
+      for (int st = 0; st <= NH; ++st) {  // stage st: theta_st (Zf) -> a_st
+        TT(b3);
         mbar_wait(&bar_b, ph_b);
         ph_b ^= 1;
         tc_fence_after();
-        fwd_epilogue(0, j);
-        if (j < NH) signal(&bar_rb);
+        TT(b4);
+        TACC(2, b4 - b3);
+        unsigned char* dst = sRing + slot(p, st);
+        float v[2][16];
+        tmem_ld16(my_tmem, v[0]);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < CPT) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
+          float* vc = v[c & 1];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
+          store_chunk16(dst, r, c_base + c, vc);
+          if (st == NH) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
+              ypart = fmaf(w4.x, vc[i], ypart); ypart = fmaf(w4.y, vc[i + 1], ypart);
+              ypart = fmaf(w4.z, vc[i + 2], ypart); ypart = fmaf(w4.w, vc[i + 3], ypart);
+            }
+          }
+        }
+        if (st < NH) signal(&bar_rb);
+        { TT(b5); TACC(3, b5 - b4); }
       }
-      loss_phase(0);
-      xb = xf;
-      cur = 0;
+      TT(b6);
+      // ---- loss (datal2, main.py:176-182), scaled output gradient and dz_NH
+      if (CG > 1) {
+        s_y[cg][r] = ypart;
+        named_bar_sync(1, GT);
+      }
+      // every thread of the row forms y, the error and dy itself (same operands, same order: identical values);
+      // column group 0 additionally accumulates the loss and writes the dWlast operand block
+      float y = s_bl[0];
+      if (CG > 1) {
+#pragma unroll
+        for (int c = 0; c < CG; ++c) y += s_y[c][r];
+      } else {
+        y += ypart;
+      }
+      float dys = 0.f;
+      if (s_begin + (long long)k * kTile + r < s_end) {
+        const float e = y - xf.w;  // xf.w: the row's normalised target
+        const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : s_gw[p][r];
+        if (cg == 0) loss_acc = fmaf(wt * e, e, loss_acc);
+        dys = kGradScale * wt * e;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_gfree[p]);  // staging slot consumed (target and weight are in registers)
+      TT(b7);
+      if (k >= 1) mbar_wait(&bar_f1, (uint32_t)(k - 1) & 1);  // dW_1 of tile k-1 done: dz buffer sb is free
+      TT(b8);
+      TACC(4, b7 - b6); TACC(5, b8 - b7);
+      if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
+      dys *= wh;
+      {
+        unsigned char* dzb = sDz + (size_t)sb * BUF;
+        float v[2][16];
+        tmem_ld16(my_tmem, v[0]);  // theta_NH is still in Zf: the next forward MMA is issued after this signal
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < CPT) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
+          float* vc = v[c & 1];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
+            vc[i] = dys * w4.x * fast_cos(vc[i]); vc[i + 1] = dys * w4.y * fast_cos(vc[i + 1]);
+            vc[i + 2] = dys * w4.z * fast_cos(vc[i + 2]); vc[i + 3] = dys * w4.w * fast_cos(vc[i + 3]);
+          }
+          store_chunk16_sat(dzb, r, c_base + c, vc);
+        }
+      }
+      signal(&bar_lb);  // the "loss done" event
+      sb ^= sb_flip;
+      { TT(b9); TACC(6, b9 - b8); }
     }
-    TT(e_start);
-    for (int i = 0; i < n_tiles; ++i) {  // tile i walks backward, tile i+1 forward (ring parity pb)
-      const int pb = (i & 1) ^ 1;
-      const bool has_b = i + 1 < n_tiles;
-      TT(e0);
-      if (has_b) fwd_prologue(i + 1);
-      signal(&bar_ra);
-      TT(e1);
-      TACC(0, e1 - e0);
-      for (int j = 1; j <= NH; ++j) {
-        const int l = NH + 1 - j;
-        // -- backward tile
-        TT(e2);
+    { TT(b_end); TACC(7, b_end - b_start); TACC(8, n_tiles); }
+  } else {
+    // ============================================ group A: backward =============================================
+    uint32_t ph_a = 0;
+    int sb = 0;
+    const float w0_over_wh = w0 / wh;
+    TT(a_start);
+    for (int k = 0; k < n_tiles; ++k) {
+      for (int ia = 0; ia < NH; ++ia) {  // stage l = NH - ia: dz_{l-1} = dX_{l-1} * w * cos(theta_{l-1})
+        const int l = NH - ia;
+        TT(a0);
         mbar_wait(&bar_a, ph_a);
         ph_a ^= 1;
         tc_fence_after();
-        TT(e3);
-        bwd_epilogue(l);
-        signal(&bar_ra);
-        TT(e4);
-        TACC(1, e3 - e2); TACC(2, e4 - e3);
-        // -- forward tile
-        if (has_b) {
-          mbar_wait(&bar_b, ph_b);
-          ph_b ^= 1;
-          tc_fence_after();
-          TT(e5);
-          fwd_epilogue(pb, j);
-          if (j < NH) signal(&bar_rb);
-          TT(e6);
-          TACC(3, e5 - e4); TACC(4, e6 - e5);
+        TT(a1);
+        if (ia == 0) TACC(0, a1 - a0); else TACC(1, a1 - a0);
+        unsigned char* dzb = sDz + (size_t)(sb ^ ((ia + 1) & 1)) * BUF;  // dz_{l-1}
+        const float scale = l >= 2 ? 1.0f : w0_over_wh;  // dX carries w_hidden (omega-scaled weights); layer 0 wants w_0
+        float vz[2][16], vx[2][16];
+        const uint32_t tz = my_tmem + F + (uint32_t)(l & 1) * zb_stride, tx = my_tmem + 2 * F + zb_stride;
+        tmem_ld16(tz, vz[0]);
+        tmem_ld16(tx, vx[0]);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < CPT) {
+            tmem_ld16(tz + 16 * (c + 1), vz[(c + 1) & 1]);
+            tmem_ld16(tx + 16 * (c + 1), vx[(c + 1) & 1]);
+          }
+          float* z = vz[c & 1];
+          const float* x = vx[c & 1];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
+          store_chunk16_sat(dzb, r, c_base + c, z);
         }
+        TT(a2);
+        signal(&bar_ra);
+        TT(a3);
+        TACC(2, a2 - a1); TACC(3, a3 - a2);
       }
-      TT(e7);
-      mbar_wait(&bar_a, ph_a);  // tile i is done: its ring slots, sX and sDz may be reused
-      ph_a ^= 1;
-      tc_fence_after();
-      TT(e8);
-      if (has_b) {
-        loss_phase(i + 1);
-        xb = xf;
-        cur = 0;
-      }
-      TT(e9);
-      TACC(5, e8 - e7); TACC(6, e9 - e8);
+      sb ^= sb_flip;
     }
-    { TT(e_end); TACC(7, e_end - e_start); TACC(8, n_tiles); }
+    { TT(a_end); TACC(7, a_end - a_start); TACC(8, n_tiles); }
   }
   __syncthreads();
 
   // ---- slice epilogue: loss partial + gradient partials (TMEM -> global), scale removed in fp32
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
-  if (cg == 0) {
+  if (warp < GW && cg == 0) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
     if (lane == 0) s_red[q] = loss_acc;
@@ -791,39 +810,41 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   // The slot image (padded device layout, pads zero) is assembled in shared memory — the operand buffers are dead
   // by now — and leaves with coalesced 16-byte stores; scattered 4-byte stores from the accumulator rows cost ~10 us.
   float* img = reinterpret_cast<float*>(smem);
-  for (int i = t; i < n.P_dev; i += TcCfg<F>::FIT_THREADS) img[i] = 0.f;
+  for (int i = t; i < n.P_dev; i += C::THREADS) img[i] = 0.f;
   __syncthreads();
   if (t == 0) a.loss_partials[n.slice_off + slice] = (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]) * inv_count;
-  if (n_tiles > 0 && warp < NW) {
+  if (n_tiles > 0 && warp < 4 * NC) {  // warp w: lane quadrant w & 3, 16-column chunk w >> 2 of every accumulator block
     const float unscale = 2.0f * inv_count / kGradScale;
     // lanes 0..15 of a quadrant hold the even accumulator of a block, lanes 16..31 the odd one; row = 16q + lane%16
+    const int ch = warp >> 2;
     const int o = q * 16 + (lane & 15), half = lane >> 4;
     const int F4 = n.F4;
     const int n_blocks = fit_acc_blocks(NH);
+    const uint32_t base = tm + ((uint32_t)(32 * q) << 16) + 16 * ch + acc0;
     float v[16];
     for (int b = 0; b < n_blocks; ++b) {
       const int i = 2 * b + half;  // accumulator index served by this thread in block b
-      tmem_ld16(my_tmem + 3 * F + b * F, v);
+      tmem_ld16(base + b * F, v);
       tmem_ld_wait();
       if (i < NH) {  // dW_{i+1}, db_{i+1}
         if (o < f) {
           const int l = i + 1;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            const int k = 16 * cg + c;
+            const int k = 16 * ch + c;
             if (k < f) img[dl_W(n, l) + o * F4 + k] = v[c] * unscale;
             else if (k == f) img[dl_b(n, l) + o] = v[c] * unscale;
           }
         }
       } else if (i == NH) {  // dW0 block
-        if (cg == 0 && o < f) {
+        if (ch == 0 && o < f) {
           img[dl_W0(n) + 4 * o + 0] = (v[0] + v[4]) * unscale;
           img[dl_W0(n) + 4 * o + 1] = (v[1] + v[5]) * unscale;
           if (n.in_dim == 3) img[dl_W0(n) + 4 * o + 2] = (v[2] + v[6]) * unscale;
           img[dl_b0(n) + o] = v[3] * unscale;
         }
       } else if (i == NH + 1) {  // dWlast block: row = feature of a_NH, column 0; row f is dblast
-        if (cg == 0) {
+        if (ch == 0) {
           if (o < f) img[dl_Wlast(n) + o] = v[0] * unscale;
           else if (o == f) img[dl_blast(n)] = v[0] * unscale;
         }
@@ -834,7 +855,7 @@ __global__ void __launch_bounds__(TcCfg<F>::FIT_THREADS, TcCfg<F>::FIT_MIN_BLOCK
   {
     float4* dst = reinterpret_cast<float4*>(a.partials + n.part_off + (long long)slice * n.P_dev);
     const float4* src = reinterpret_cast<const float4*>(img);
-    for (int i = t; i < (n.P_dev >> 2); i += TcCfg<F>::FIT_THREADS) dst[i] = src[i];
+    for (int i = t; i < (n.P_dev >> 2); i += C::THREADS) dst[i] = src[i];
   }
   tc_fence_before();
   __syncthreads();
@@ -866,7 +887,7 @@ size_t tc_fit_smem(int F, int L) {  // sDz[2] + ring[NS + 2] + sX[2] + sDY + ima
 
 // resident fit CTAs per SM: the launch bound (registers), shared memory (dynamic + ~8 KB static) and TMEM columns
 int tc_fit_ctas_per_sm(int F, int L) {
-  const int by_bound = F >= 48 ? 1 : F == 32 ? 2 : 4;  // == TcCfg<F>::FIT_MIN_BLOCKS
+  const int by_bound = F >= 48 ? 1 : F == 32 ? 2 : 3;  // == FitCfg<F>::MIN_BLOCKS
   const size_t dyn = tc_fit_smem(F, L) < 49152 ? 49152 : tc_fit_smem(F, L);
   const int by_smem = (int)((size_t)227 * 1024 / (dyn + 8192));
   const int by_tmem = 512 / fit_tmem_cols(F, L - 2);
@@ -879,7 +900,7 @@ bool tc_supported(int f, int L, int in_dim, int out_dim) {
   const int F = tc_fpad(f);
   if (out_dim != 1 || (in_dim != 2 && in_dim != 3)) return false;
   if (L < 3 || F > 64) return false;
-  if (3 * F + fit_acc_blocks(L - 2) * F > 512) return false;  // TMEM: Zf, Zb, Xb + packed dW accumulators
+  if (3 * F + fit_acc_blocks(L - 2) * F > 512) return false;  // TMEM: Zf, Zb (x2 if it fits), Xb + packed dW accumulators
   if (tc_fit_smem(F, L) > 221 * 1024) return false;           // + ~5 KB static shared memory <= 227 KB
   if (tc_eval_groups(F, L) < 1) return false;
   return true;
@@ -919,7 +940,7 @@ static cudaError_t launch_fit_f(const FitArgs& a, int L_max, int n_blocks, cudaS
   const size_t smem = tc_fit_smem(F, L_max) < 49152 ? 49152 : tc_fit_smem(F, L_max);
   cudaError_t e = cudaFuncSetAttribute(tc_fit_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tc_fit_kernel<F><<<n_blocks, TcCfg<F>::FIT_THREADS, smem, st>>>(a);
+  tc_fit_kernel<F><<<n_blocks, FitCfg<F>::THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -1,18 +1,8 @@
-"""Per-stage cycle accounting of tc_fit_kernel (CTA 0): builds a second library with -DBRIEF_TC_TIMING and prints where
-an epilogue warp, the MMA-issue warp and the sampler warp spend their cycles.
-    python tools/tc_stage_timing.py [features] [layers] [batch] [nets]      (on a GPU box)"""
-import ctypes, os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-from brief_pytorch_b200 import build as _b
-lib = os.path.join(_b.LIBDIR, "libbrief_timing.so")
-flags = [f for f in _b.NVCC_FLAGS if f != "--use_fast_math=false"]
-if "--no-build" not in sys.argv:
-    subprocess.run([_b._nvcc(), *flags, "-DBRIEF_TC_TIMING", "-o", lib] + [os.path.join(_b.CSRC, s) for s in _b.SOURCES], check=True)
-if "--build-only" in sys.argv:
-    sys.exit(0)
-os.environ["BRIEF_NO_BUILD"] = "1"
-_b.LIBPATH = lib
+"""Per-role cycle accounting of tc_fit_kernel (CTA 0): first warp of group B (forward), first warp of group A
+(backward), the MMA-issue warp.  Needs a library built with -DBRIEF_TC_TIMING:
+    python tools/exp_variant.py timing "-DBRIEF_TC_TIMING" -- tools/tc_stage_timing.py [features] [layers] [batch] [nets]"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from brief_pytorch_b200 import _cabi
 from brief_pytorch_b200.group import NetSpec, SirenGroup, pack_module_params
@@ -43,18 +33,16 @@ print(f"f={f} L={L} batch={batch} nets={nets}: {e0.elapsed_time(e1) / n_runs * 1
 l.brief_debug_read_timing(buf, 0)
 v = list(buf)
 NH = L - 2
-tiles = max(1, v[8])
-print(f"epilogue warp 0 (CTA 0): {tiles / n_runs:.0f} tiles per launch; cycles per tile:")
-for i, nme in enumerate(["fwd_prologue+signal", "wait A (z,dX)", "bwd_epilogue+signal", "wait B (fwd)", "fwd_epilogue+signal",
-                         "wait A (tile end)", "loss_phase", "TOTAL"]):
-    per = NH if 1 <= i <= 4 else 1
-    print(f"   {nme:22s} {v[i] / tiles:9.1f}   ({v[i] / tiles / per:7.1f} per stage)" if per > 1 else f"   {nme:22s} {v[i] / tiles:9.1f}")
-mt = max(1, v[16 + 7])
-print("MMA warp: cycles per tile:")
-for i, nme in enumerate(["wait ra (tile start)", "issue bwd NH + fwd 1", "wait ra (stage)", "issue bwd stage", "wait rb (stage)",
-                         "issue fwd stage", "TOTAL"]):
-    print(f"   {nme:22s} {v[16 + i] / mt:9.1f}")
-st = max(1, v[32 + 7])
-print("sampler warp: cycles per tile:")
-for i, nme in enumerate(["wait gfree", "sample_tile"]):
-    print(f"   {nme:22s} {v[32 + i] / st:9.1f}")
+def show(title, base, names, tiles):
+    print(f"{title}: cycles per tile ({tiles / n_runs:.0f} tiles per launch)")
+    for i, nme in enumerate(names):
+        if nme:
+            print(f"   {nme:34s} {v[base + i] / tiles:9.1f}")
+tb = max(1, v[8])
+show("group B (forward) warp 0", 0, ["wait f2 (tile k-2 done)", "wait sampler", f"wait MMA x{NH + 1}", f"sine epilogue x{NH + 1}",
+                                    "y exchange + loss", "wait f1 (dz buffer free)", "dz_NH + signal", "TOTAL"], tb)
+ta = max(1, v[16 + 8])
+show("group A (backward) warp 0", 16, ["wait MMA (first stage of tile)", f"wait MMA x{NH - 1}", f"cos epilogue x{NH}", f"signal x{NH}", "", "", "", "TOTAL"], ta)
+tm = max(1, v[32 + 6])
+print(f"MMA warp: cycles per tile: A batches {v[32] / tm:.1f} ({v[33] / tm:.1f} batches), B batches/events {v[34] / tm:.1f} ({v[35] / tm:.1f}), "
+      f"idle polls {v[36] / tm:.1f}, TOTAL {v[37] / tm:.1f}")
