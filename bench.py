@@ -321,15 +321,38 @@ def main():
         host_loss = torch.empty(n_local, dtype=torch.float32).pin_memory()
         h2d, d2h = 0, n_local * 4
 
+    # step s+1's indices cross PCIe on a copy stream while step s computes (two device buffers); every step still moves
+    # its own h2d bytes and reads its own loss back before the next one starts
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    idx_buf = [torch.empty_like(dev_idx) for _ in range(2)] if host_idx is not None else None
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(s):
+        if host_idx is None:
+            return
+        k = s & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[k])
+            idx_buf[k].copy_(host_idx[s % 8], non_blocking=True)
+            ready[k].record(copy_stream)
+
     def e2e_step(s):
+        k = s & 1
+        prefetch(s + 1)
         if host_idx is not None:
-            dev_idx.copy_(host_idx[s % 8], non_blocking=True)
-        loss = grp.fit_step(dev_idx, seed=42, step=s)
+            main_stream.wait_event(ready[k])
+        loss = grp.fit_step(idx_buf[k] if host_idx is not None else None, seed=42, step=s)
         grp.opt_step("Adamax", 1e-3)
+        consumed[k].record(main_stream)
         host_loss.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the loss is read on the host every step, like loss.item()
+        main_stream.synchronize()  # the loss is read on the host every step, like loss.item()
         return host_loss
 
+    for k in range(2):
+        consumed[k].record(main_stream)
+    prefetch(0)
     for s in range(args.warmup):
         e2e_step(s)
     barrier()
@@ -396,8 +419,8 @@ def main():
                              "ms_per_step": 1e3 * t_b2b / args.steps, "note": "no L2 flush, one event pair around K steps"},
             "e2e": {"value": samples_per_step * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "note": "per step: pinned host sampler indices -> device, fit_step + opt_step via the Python API, "
-                            "per-block loss -> host"},
+                    "note": "per step: pinned host sampler indices -> device (copy stream, one step ahead), fit_step + "
+                            "opt_step via the Python API, per-block loss -> host + sync"},
             "gpu_launches": int(launches_total),
             "roofline": {"bound": "tensor", "achieved": tf_kernel, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": tf_kernel / peak_tf,

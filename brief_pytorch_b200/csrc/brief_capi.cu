@@ -380,8 +380,11 @@ int launch_opt_kernel(BriefGroup* g, bool from_partials, bool apply, int kind, d
       o.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(b2, (double)t));
     }
   }
+  // the optimiser refreshes the fp16 operand image itself (image_scatter) — unless the image is already stale, in
+  // which case the next ensure_wpack() rebuilds it from the parameters anyway
+  if (apply && g->total_wpack > 0 && !g->wpack_dirty) o.wpack = g->d_wpack.p;
   LAUNCH(launch_opt(o, g->opt.blocks, st));
-  if (apply) g->wpack_dirty = true;
+  if (apply && !o.wpack) g->wpack_dirty = true;
   return 0;
 }
 

@@ -23,6 +23,58 @@ namespace brief {
 
 constexpr int kOptThreads = 256;
 
+__device__ __forceinline__ __half hi16(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ __half lo16(float x) { return __float2half_rn(__fsub_rn(x, __half2float(__float2half_rn(x)))); }
+
+// Refresh the entries of the fp16 operand image (brief_image.cuh) that depend on parameter i (padded device layout) —
+// the same values pack_kernel writes, so the optimiser step leaves the image current and the fit loop needs no
+// separate pack launch.  Constant entries (pi/2 rows, zero pads) are written once by pack_kernel.
+__device__ __forceinline__ void image_scatter(const NetDev& n, unsigned char* img, int i, float p) {
+  const int F = n.F_PAD, NH = n.L - 2, f = n.f, F4 = n.F4;
+  auto put = [&](size_t off, __half h) { *reinterpret_cast<__half*>(img + off) = h; };
+  float* side = reinterpret_cast<float*>(img + img_side_off(F, NH));
+  if (i < 4 * F4) {  // W0 [F4][4]
+    const int o = i >> 2, c = i & 3;
+    if (o >= f || c >= 3) return;
+    const float v = __fmul_rn(n.w0, p);
+    const size_t base = img_l0_off(F, NH);
+    put(base + img_elem_off(o, c, F), hi16(v));
+    put(base + img_elem_off(o, c + 4, F), hi16(v));
+    put(base + img_elem_off(o, c + 8, F), lo16(v));
+    side[4 * o + c] = p;
+  } else if (i < 5 * F4) {  // b0
+    const int o = i - 4 * F4;
+    if (o >= f) return;
+    const float v = __fmul_rn(n.w0, p);
+    const size_t base = img_l0_off(F, NH);
+    put(base + img_elem_off(o, 3, F), hi16(v));
+    put(base + img_elem_off(o, 7, F), lo16(v));
+    side[4 * o + 3] = p;
+  } else if (i < dl_Wlast(n)) {  // hidden layers
+    const int per = F4 * F4 + F4;
+    const int j = i - 5 * F4, l = j / per, r = j - l * per;
+    const size_t base = (size_t)l * F * F * 2;
+    const float v = __fmul_rn(n.wh, p);
+    if (r < F4 * F4) {
+      const int o = r / F4, k = r - o * F4;
+      if (o < f && k < f) put(base + img_elem_off(o, k, F), hi16(v));
+    } else {
+      const int o = r - F4 * F4;
+      if (o >= f) return;
+      put(base + img_elem_off(o, f, F), hi16(v));
+      put(base + img_elem_off(o, f + 1, F), lo16(v));
+      side[4 * F + l * F + o] = v;
+    }
+  } else {  // Wlast [F4], blast
+    const int k = i < dl_blast(n) ? i - dl_Wlast(n) : (i == dl_blast(n) ? f : -1);
+    if (k < 0 || (i < dl_blast(n) && k >= f)) return;
+    const size_t base = img_last_off(F, NH);
+    put(base + img_elem_off(0, k, 16), hi16(p));
+    put(base + img_elem_off(1, k, 16), lo16(p));
+    if (k < f) side[4 * F + NH * F + k] = p; else side[4 * F + NH * F + F] = p;
+  }
+}
+
 __global__ void __launch_bounds__(kOptThreads) opt_kernel(OptArgs a) {
   // locate network: blk_prefix has n_nets+1 entries
   int lo = 0, hi = a.n_nets;
@@ -80,6 +132,7 @@ __global__ void __launch_bounds__(kOptThreads) opt_kernel(OptArgs a) {
     a.v[gi] = v;
   }
   a.params[gi] = p;
+  if (a.wpack && n.prec == 1) image_scatter(n, a.wpack + n.wpack_off, i, p);
 }
 
 cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st) {
@@ -88,8 +141,6 @@ cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st) {
 }
 
 // ---- fp16 operand image for the tcgen05 kernels (layout: brief_image.cuh) -----------------------------------------
-__device__ __forceinline__ __half hi16(float x) { return __float2half_rn(x); }
-__device__ __forceinline__ __half lo16(float x) { return __float2half_rn(__fsub_rn(x, __half2float(__float2half_rn(x)))); }
 
 __global__ void pack_kernel(const NetDev* nets, int n_nets, const float* __restrict__ params, unsigned char* wpack) {
   constexpr float kHalfPi = 1.57079632679f;

@@ -279,3 +279,31 @@ def test_full_size_block_properties(prec):
     assert np.isfinite(hist).all() and hist[-10:].mean() < hist[:10].mean()
     dec = u16(grp.decompress("uint16")[0])
     assert dec.min() >= vol.min() and dec.max() <= vol.max()
+
+
+@pytest.mark.parametrize("optname", ["Adamax", "SGD"])
+@pytest.mark.parametrize("tag", ["c1", "c2", "c2small", "img2d"])
+def test_operand_image_refreshed_by_the_optimiser_equals_a_full_pack(tag, optname):
+    """The optimiser kernel rewrites the fp16 operand image entry by entry (image_scatter); a group that gets the
+    same parameters through set_params() builds the image with pack_kernel.  Both must decode to identical bits."""
+    from brief_pytorch_b200 import Networks
+    from brief_pytorch_b200.group import pack_module_params
+    kw = NETS[tag]
+    dims = (6, 20, 24) if kw["coords_channel"] == 3 else (40, 36)
+    torch.manual_seed(3)
+    phi = Networks.init_phi(dict(kw, data_channel=1, name="SIREN"))
+    rng = np.random.default_rng(5)
+    vol = rng.integers(100, 30000, size=dims, dtype=np.uint16)[..., None]
+    grp = make_group([spec_of(kw, dims)], "f16")
+    grp.set_axes(0, "-1,1")
+    grp.set_params(0, pack_module_params(phi))
+    bind_block(grp, 0, vol, rules=[(65535, 65535, 1.0)], tau=0.0)
+    grp.set_sampler(0, "randomcube")
+    grp.fit_run(7, optname, 1e-3 if optname == "Adamax" else 1e-6, seed=1)   # image kept current by the optimiser
+    a = grp.decompress("float32")[0].cpu().numpy()
+    fresh = make_group([spec_of(kw, dims)], "f16")
+    fresh.set_axes(0, "-1,1")
+    fresh.set_params(0, grp.get_params(0))                                    # image rebuilt by pack_kernel
+    b = fresh.decompress("float32")[0].cpu().numpy()
+    assert a.tobytes() == b.tobytes()
+    assert np.isfinite(a).all()
