@@ -391,6 +391,26 @@ def main():
     torch.cuda.synchronize()
     t_dec_e2e = time.perf_counter() - t0
 
+    # ---- NCCL, after the hot path: decoded blocks -> rank 0 (variable-size send/recv), checked by a checksum table ----
+    gather = None
+    if world > 1:
+        local_dec = {b: outs[j] for j, b in enumerate(mine)}
+        shapes = [bs] * n_total
+        sums = torch.stack([o.view(torch.int16).to(torch.int64).sum() for o in outs]).to(torch.float64).reshape(-1, 1)
+        want = sharding.gather_block_stats(sums, owner)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        got = sharding.gather_blocks(local_dec, owner, shapes, dst=0)
+        g1.record()
+        barrier()
+        t_gather = g0.elapsed_time(g1) / 1e3
+        if rank == 0:
+            ok = all(float(got[b].view(torch.int16).to(torch.int64).sum()) == float(want[b, 0]) for b in range(n_total))
+            nbytes = sum(int(np.prod(bs)) * 2 for b in range(n_total) if owner[b] != 0)
+            gather = {"ms": 1e3 * t_gather, "bytes_into_rank0": nbytes, "gbs": nbytes / t_gather / 1e9, "checksums_ok": ok}
+        del got
+
     # ---- reduce over ranks (max time), gather per-block stats (the only collective; outside the timed region) ----
     times = torch.tensor([t_dev, t_b2b, t_e2e, t_kernel, t_dec, t_dec_e2e], dtype=torch.float64, device=dev)
     counts = torch.tensor([samples_per_step_local, vox_local, launches], dtype=torch.float64, device=dev)
@@ -434,6 +454,8 @@ def main():
                            "tensor_frac": vox_total / world * fwd_flops / t_dec / 1e12 / peak_tf},
             "final_loss_mean": float(table.mean()), "clocks": clk,
         }
+        if gather is not None:
+            line["gather_decoded_blocks"] = gather
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             step = oracle_fit_rate(plan, args.cpu_seconds, threads)
