@@ -196,7 +196,7 @@ struct TableBuilder {
 int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   int tm = 128;
   for (auto& n : g->nets) {
-    if (n.prec == BRIEF_PREC_F16) continue;
+    if (n.eval_tc) continue;
     const int t = simt_pick_tm(n.F4, n.L, false, kSmemLimit);
     if (t == 0)
       return fail(BRIEF_ERR_UNSUPPORTED, "features=%d exceed the fp32 kernel's shared-memory budget", n.f);
@@ -208,11 +208,11 @@ int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
   long long bucket_tiles[kBuckets] = {0};
   for (const auto& n : g->nets)
-    if (n.prec == BRIEF_PREC_F16) bucket_tiles[n.F_PAD / 16] += (n.n_vox + kTcTile - 1) / kTcTile;
+    if (n.eval_tc) bucket_tiles[n.F_PAD / 16] += (n.n_vox + kTcTile - 1) / kTcTile;
   for (int b = 1; b < kBuckets; ++b) g->tc_eval_tpb[b] = tc_eval_tpb(bucket_tiles[b], g->num_sms);
   for (int i = 0; i < g->n_nets; ++i) {
     const NetDev& n = g->nets[i];
-    if (n.prec == BRIEF_PREC_F16) {
+    if (n.eval_tc) {
       const int b = n.F_PAD / 16;
       const long long tiles = (n.n_vox + kTcTile - 1) / kTcTile;
       const long long blocks = (tiles + g->tc_eval_tpb[b] - 1) / g->tc_eval_tpb[b];
@@ -481,7 +481,10 @@ int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device
                        "net %d: features=%d layers=%d is outside the fused tcgen05 kernel's TMEM/SMEM budget; "
                        "use BRIEF_PREC_FP32 or BRIEF_PREC_AUTO", i, n.f, n.L));
     n.prec = (precision == BRIEF_PREC_FP32 || !tc_ok) ? BRIEF_PREC_FP32 : BRIEF_PREC_F16;
-    if (n.prec == BRIEF_PREC_F16) {
+    // forward / decompress have a wider tensor-core envelope than the fit (no activation ring): AUTO uses it
+    n.eval_tc = (n.prec == BRIEF_PREC_F16 ||
+                 (precision == BRIEF_PREC_AUTO && tc_eval_supported(n.f, n.L, n.in_dim, n.out_dim))) ? 1 : 0;
+    if (n.eval_tc) {
       n.F_PAD = tc_fpad(n.f);
       n.wpack_off = (long long)g->total_wpack;
       g->total_wpack += (tc_wpack_bytes(n.F_PAD, n.L) + 127) & ~(size_t)127;
@@ -729,7 +732,7 @@ int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n
   a.out_f32 = dev_out;
   a.layers_out = dev_layers;
   a.wpack = g->d_wpack.p;
-  if (nd.prec == BRIEF_PREC_F16) {
+  if (nd.eval_tc) {
     RC(ensure_wpack(g, st));
     const long long tiles = (n + kTcTile - 1) / kTcTile;
     a.tiles_per_block = tc_eval_tpb(tiles, g->num_sms);

@@ -55,8 +55,9 @@ struct NetDev {
   long long slice_off;         // first loss-partial slot of this network
   long long part_off;          // floats, into the gradient-partials arena (n_slices slots of P_dev)
   // tensor-core path
-  int prec;                    // resolved BriefPrecision
-  int F_PAD;                   // padded width of the fp16 operand image (multiple of 16, > f)
+  int prec;                    // resolved BriefPrecision of the FIT path
+  int eval_tc;                 // 1: forward / decompress run on the tensor core (an operand image exists)
+  int F_PAD;                   // padded width of the fp16 operand image (multiple of 16, >= f + 2)
   long long wpack_off;         // bytes, into the fp16 packed-weight arena
 };
 

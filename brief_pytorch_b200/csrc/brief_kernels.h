@@ -30,6 +30,7 @@ struct EvalArgs {
   // tensor-core path only
   const unsigned char* wpack;
   int tiles_per_block;  // 128-sample tiles served by one CTA (split round-robin over its groups)
+  int eval_slots;       // tile slots per group (2, or 1 for the widest networks)
 };
 
 // Fit work: block b serves slice (b - work_prefix[i]) of network work_net[i].
@@ -93,6 +94,8 @@ int tc_fit_ctas_per_sm(int F_PAD, int L);
 size_t tc_wpack_bytes(int F_PAD, int L);
 size_t tc_eval_smem(int F_PAD, int L);
 int tc_eval_groups(int F_PAD, int L);
+int tc_eval_slots(int F_PAD, int L);
+bool tc_eval_supported(int f, int L, int in_dim, int out_dim);
 size_t tc_fit_smem(int F_PAD, int L);
 cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st);
 cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st);

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kOptThreads) opt_kernel(OptArgs a) {
     a.v[gi] = v;
   }
   a.params[gi] = p;
-  if (a.wpack && n.prec == 1) image_scatter(n, a.wpack + n.wpack_off, i, p);
+  if (a.wpack && n.eval_tc) image_scatter(n, a.wpack + n.wpack_off, i, p);
 }
 
 cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st) {
@@ -146,7 +146,7 @@ __global__ void pack_kernel(const NetDev* nets, int n_nets, const float* __restr
   constexpr float kHalfPi = 1.57079632679f;
   for (int net_id = blockIdx.y; net_id < n_nets; net_id += gridDim.y) {
   const NetDev& n = nets[net_id];
-  if (n.prec != 1) continue;
+  if (!n.eval_tc) continue;
   const int F = n.F_PAD, NH = n.L - 2, f = n.f, F4 = n.F4;
   const float* P = params + n.param_off;
   unsigned char* img = wpack + n.wpack_off;

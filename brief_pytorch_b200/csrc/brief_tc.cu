@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
   __shared__ uint32_t tmem_base_s;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int G = (blockDim.x - 32) >> 7, U = G * kEvalSlots;
+  const int G = (blockDim.x - 32) >> 7, S = a.eval_slots, U = G * S;  // S tile slots per group (2; 1 when F is wide)
   const bool mma_warp = warp == 4 * G;
   const int g = warp >> 2, q = warp & 3, r = 32 * q + lane;
   int net_id;
@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
     constexpr uint32_t idesc_f = make_idesc(128, F, false, false);
     for (int it = 0; it < rounds; ++it)
       for (int st = 0; st < steps; ++st) {
-        for (int slot = 0; slot < kEvalSlots; ++slot)
+        for (int slot = 0; slot < S; ++slot)
           for (int gi = 0; gi < G; ++gi) {
-            const int u = gi * kEvalSlots + slot;
+            const int u = gi * S + slot;
             if (it * U + u >= count) continue;  // this unit has no tile in the last round
             mbar_wait(&bar_r[u], ph);
             tc_fence_after();
@@ -272,13 +272,13 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
     const float inv_w0 = 1.0f / n.w0, inv_wh = 1.0f / n.wh;
     uint32_t phase = 0;  // both slots wait the same number of times per round
     for (int it = 0; it < rounds; ++it) {
-      const int u0 = g * kEvalSlots;
+      const int u0 = g * S;
       bool act[kEvalSlots], valid[kEvalSlots];
       long long sidx[kEvalSlots];
 #pragma unroll
       for (int slot = 0; slot < kEvalSlots; ++slot) {
         const int u = u0 + slot;
-        act[slot] = it * U + u < count;
+        act[slot] = slot < S && it * U + u < count;
         sidx[slot] = (tile_begin + (long long)it * U + u) * kTile + r;
         valid[slot] = act[slot] && sidx[slot] < total;
       }
@@ -868,18 +868,33 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 int tc_fpad(int f) { return ((f + 2 + 15) / 16) * 16; }  // two constant-one columns (bias hi / lo)
 
 size_t tc_wpack_bytes(int F, int L) { return img_bytes(F, L - 2); }
-// groups per CTA (two tile slots each): TMEM columns (2 G F <= 512) and shared memory (image + 2 G unit buffers)
-int tc_eval_groups(int F, int L) {
+// groups per CTA and tile slots per group: TMEM columns (G S F <= 512) and shared memory (image + G S unit buffers)
+static void eval_shape(int F, int L, int* groups, int* slots) {
   const size_t img = img_bytes_padded(F, L - 2);
   const size_t budget = (F <= 32 ? (size_t)110 : (size_t)224) * 1024;  // F <= 32: two CTAs per SM
-  if (img + kEvalSlots * eval_unit_bytes(F) > budget) return 0;
-  int g = (int)((budget - img) / (kEvalSlots * eval_unit_bytes(F)));
-  g = g < kEvalMaxGroups ? g : kEvalMaxGroups;
-  g = g < 512 / (kEvalSlots * F) ? g : 512 / (kEvalSlots * F);
-  return g;
+  *groups = 0;
+  *slots = 0;
+  if (img + eval_unit_bytes(F) > budget) return;
+  int units = (int)((budget - img) / eval_unit_bytes(F));
+  units = units < 512 / F ? units : 512 / F;
+  if (units >= 2) {
+    *slots = kEvalSlots;
+    *groups = units / kEvalSlots < kEvalMaxGroups ? units / kEvalSlots : kEvalMaxGroups;
+  } else {
+    *slots = 1;
+    *groups = 1;
+  }
 }
+int tc_eval_groups(int F, int L) { int g, s; eval_shape(F, L, &g, &s); return g; }
+int tc_eval_slots(int F, int L) { int g, s; eval_shape(F, L, &g, &s); return s; }
 size_t tc_eval_smem(int F, int L) {
-  return img_bytes_padded(F, L - 2) + (size_t)tc_eval_groups(F, L) * kEvalSlots * eval_unit_bytes(F);
+  return img_bytes_padded(F, L - 2) + (size_t)tc_eval_groups(F, L) * tc_eval_slots(F, L) * eval_unit_bytes(F);
+}
+// forward / decompress on the tensor core: any width whose padded image + one tile fit (f <= 126 at L = 7)
+bool tc_eval_supported(int f, int L, int in_dim, int out_dim) {
+  const int F = tc_fpad(f);
+  if (out_dim != 1 || (in_dim != 2 && in_dim != 3) || L < 3 || F > 128) return false;
+  return tc_eval_groups(F, L) >= 1;
 }
 size_t tc_fit_smem(int F, int L) {  // sDz[2] + ring[NS + 2] + sX[2] + sDY + image
   return (size_t)(2 + (L - 1) + 2) * kTile * F * 2 + 3 * (size_t)kTile * 16 * 2 + img_bytes_padded(F, L - 2);
@@ -907,10 +922,12 @@ bool tc_supported(int f, int L, int in_dim, int out_dim) {
 }
 
 template <int F>
-static cudaError_t launch_eval_f(const EvalArgs& a, int L_max, int n_blocks, cudaStream_t st) {
+static cudaError_t launch_eval_f(const EvalArgs& a_in, int L_max, int n_blocks, cudaStream_t st) {
   const int G = tc_eval_groups(F, L_max);
   if (G < 1) return cudaErrorInvalidValue;
   const size_t smem = tc_eval_smem(F, L_max);
+  EvalArgs a = a_in;
+  a.eval_slots = tc_eval_slots(F, L_max);
   cudaError_t e;
   if (a.layers_out) {
     e = cudaFuncSetAttribute(tc_eval_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -930,6 +947,10 @@ cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int L_max, int n_blocks
     case 32: return launch_eval_f<32>(a, L_max, n_blocks, st);
     case 48: return launch_eval_f<48>(a, L_max, n_blocks, st);
     case 64: return launch_eval_f<64>(a, L_max, n_blocks, st);
+    case 80: return launch_eval_f<80>(a, L_max, n_blocks, st);
+    case 96: return launch_eval_f<96>(a, L_max, n_blocks, st);
+    case 112: return launch_eval_f<112>(a, L_max, n_blocks, st);
+    case 128: return launch_eval_f<128>(a, L_max, n_blocks, st);
     default: return cudaErrorInvalidValue;
   }
 }

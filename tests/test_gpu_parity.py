@@ -307,3 +307,45 @@ def test_operand_image_refreshed_by_the_optimiser_equals_a_full_pack(tag, optnam
     b = fresh.decompress("float32")[0].cpu().numpy()
     assert a.tobytes() == b.tobytes()
     assert np.isfinite(a).all()
+
+
+@pytest.mark.parametrize("features", [70, 90, 113, 126])
+def test_wide_networks_decode_on_the_tensor_core(features):
+    """Widths above the fused fit kernel's envelope (hipct f=113): under BRIEF_PREC_AUTO the fit runs the
+    fp32 CUDA-core kernels, while forward / decompress run the tcgen05 kernel (operand image kept current by the
+    optimiser).  Per-layer pre-activations and the decoded block against the oracle, f16 tolerance."""
+    from brief_pytorch_b200 import Networks
+    from brief_pytorch_b200.group import NetSpec, SirenGroup, pack_module_params
+    kw = dict(coords_channel=3, data_channel=1, layers=7, w0=10, features=features)
+    dims = (5, 24, 40)
+    torch.manual_seed(11)
+    phi = Networks.init_phi(dict(kw, name="SIREN"))
+    torch.manual_seed(11)
+    ora = O.init_phi(dict(kw, name="SIREN"))
+    grp = SirenGroup([NetSpec(features, 7, 10.0, dims)], 0, "auto")
+    assert grp.precision(0) == "fp32"          # the fit path
+    grp.set_axes(0, "-1,1")
+    grp.set_params(0, pack_module_params(phi))
+    coords = O.create_flattened_coords(dims, "-1,1")
+    y, zs = grp.forward(0, coords.cuda(), return_layers=True)
+    with torch.no_grad():
+        y_ref, z_ref, _ = O.forward_layers(O.siren_params(ora), coords, 10.0)
+    for l in range(6):
+        assert relerr(zs[l].cpu().numpy(), z_ref[l].numpy()) < TOL["f16"], f"z{l}"
+    assert relerr(y.cpu().numpy(), y_ref.numpy()) < TOL["f16"]
+    # a few optimiser steps (fp32 fit kernels) must leave the tensor-core image in sync with the parameters
+    rng = np.random.default_rng(2)
+    vol = rng.integers(1000, 30000, size=dims, dtype=np.uint16)[..., None]
+    bind_block(grp, 0, vol, rules=[(65535, 65535, 1.0)], tau=0.0)
+    grp.set_sampler(0, "randomcube")
+    grp.fit_run(3, "Adamax", 1e-3, seed=1)
+    a = grp.decompress("float32")[0].cpu().numpy()
+    fresh = SirenGroup([NetSpec(features, 7, 10.0, dims)], 0, "auto")
+    fresh.set_axes(0, "-1,1")
+    fresh.set_params(0, grp.get_params(0))
+    b = fresh.decompress("float32")[0].cpu().numpy()
+    assert a.tobytes() == b.tobytes()
+    grp.store_module(0, ora)
+    with torch.no_grad():
+        y2 = O.forward_layers(O.siren_params(ora), coords, 10.0)[0].numpy().reshape(dims)
+    assert relerr(a, y2) < TOL["f16"]
