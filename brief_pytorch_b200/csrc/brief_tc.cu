@@ -119,6 +119,21 @@ __device__ __forceinline__ void issue_dx(uint32_t d, uint32_t dz, uint32_t w) {
   for (int k = 0; k < F / 16; ++k)
     mma_f16(d, make_desc(dz + k * 2 * kActLBO, kActLBO, 128), make_desc(w + k * 2 * 128, 128, (F / 8) * 128), idesc, k > 0);
 }
+// the same two contractions with the A operand (activations / dz, fp16) in tensor memory
+template <int F>
+__device__ __forceinline__ void issue_forward_ts(uint32_t d, uint32_t a_tmem, uint32_t w) {
+  constexpr uint32_t idesc = make_idesc(128, F, false, false);
+#pragma unroll
+  for (int k = 0; k < F / 16; ++k)
+    mma_f16_ts(d, a_tmem + 8 * k, make_desc(w + k * 2 * (F / 8) * 128, (F / 8) * 128, 128), idesc, k > 0);
+}
+template <int F>
+__device__ __forceinline__ void issue_dx_ts(uint32_t d, uint32_t a_tmem, uint32_t w) {
+  constexpr uint32_t idesc = make_idesc(128, F, false, true);
+#pragma unroll
+  for (int k = 0; k < F / 16; ++k)
+    mma_f16_ts(d, a_tmem + 8 * k, make_desc(w + k * 2 * 128, 128, (F / 8) * 128), idesc, k > 0);
+}
 // issue dW[64 x N] (+)= A^T B over the 128 samples of the tile (both MN-major, K = samples)
 template <int N>
 __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_buf, uint32_t b_buf, bool accumulate) {
@@ -144,6 +159,17 @@ struct TcCfg {
   static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 4;    // must match tc_fit_ctas_per_sm()
 };
 
+// 16 fp32 -> 8 packed f16x2 words -> the operand row in shared memory and (optionally) the A-operand row in TMEM
+template <bool SAT>
+__device__ __forceinline__ void store_chunk16_both(unsigned char* buf, int r, int cg, const float* v, bool to_tmem,
+                                                   uint32_t taddr) {
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = SAT ? pack_f16x2_sat(v[2 * i], v[2 * i + 1]) : pack_f16x2(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg, kTile)) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg + 1, kTile)) = make_uint4(w[4], w[5], w[6], w[7]);
+  if (to_tmem) tmem_st8(taddr, w);
+}
 __device__ __forceinline__ void store_chunk16(unsigned char* buf, int r, int cg, const float* v) {
   *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg, kTile)) =
       make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
@@ -426,7 +452,13 @@ __host__ __device__ constexpr int fit_acc_blocks(int NH) { return (NH + 2 + 1) /
 __host__ __device__ constexpr bool fit_zb_double(int F, int NH) {
   return kFitPrefetchTheta && 4 * F + fit_acc_blocks(NH) * F <= 512;
 }
-__host__ __device__ constexpr int fit_fixed_cols(int F, int NH) { return fit_zb_double(F, NH) ? 4 * F : 3 * F; }
+// A operands of the forward and dX contractions in TMEM (F/2 columns each) when the columns allow it
+__host__ __device__ constexpr bool fit_ts_mode(int F, int NH) {
+  return (fit_zb_double(F, NH) ? 5 : 4) * F + fit_acc_blocks(NH) * F <= 512;
+}
+__host__ __device__ constexpr int fit_fixed_cols(int F, int NH) {
+  return (3 + (fit_zb_double(F, NH) ? 1 : 0) + (fit_ts_mode(F, NH) ? 1 : 0)) * F;
+}
 __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
   return tmem_cols_pow2(fit_fixed_cols(F, NH) + fit_acc_blocks(NH) * F);
 }
@@ -517,7 +549,10 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   const bool zb2 = fit_zb_double(F, NH);           // theta of backward stage l lives in Zb[l & 1] (Zb[0] if single)
   const uint32_t zb_stride = zb2 ? F : 0;
   const uint32_t acc0 = (uint32_t)fit_fixed_cols(F, NH);
+  const bool ts = fit_ts_mode(F, NH);              // A operands of forward / dX contractions live in TMEM
   const uint32_t TZF = tm, TZB = tm + F, TXB = tm + 2 * F + zb_stride;
+  const uint32_t TAF = TXB + F, TAD = TAF + F / 2;  // fp16 a_{j-1} of the forward tile | dz_l of the backward tile
+  const uint32_t my_af = TAF + ((uint32_t)(32 * q) << 16) + 8 * c_base, my_ad = TAD + ((uint32_t)(32 * q) << 16) + 8 * c_base;
   auto acc_addr = [&](int i) { return tm + acc0 + (uint32_t)(i >> 1) * F + ((uint32_t)(i & 1) << 20); };  // lane 16 = 16 << 16
   const uint32_t aDz = smem_u32(sDz), aRing = smem_u32(sRing), aX = smem_u32(sX), aDY = smem_u32(sDY), aW = smem_u32(sW);
   auto slot = [&](int parity, int j) { return (uint32_t)(parity ? R - 1 - j : j) * BUF; };  // byte offset into the ring
@@ -530,6 +565,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 
   // epilogue warp -> MMA warp: this warp's operand rows are written (and its TMEM reads are done)
   auto signal = [&](uint64_t* bar) {
+    if (ts) tmem_st_wait();
     tc_fence_before();
     fence_async_smem();
     __syncwarp();
@@ -575,7 +611,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
               else layer0(d, pa);
             };
             if (!zb2 || l == NH) recompute(l - 1);
-            issue_dx<F>(TXB, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
+            if (ts) issue_dx_ts<F>(TXB, TAD, aW + (uint32_t)(l - 1) * F * F * 2);
+            else issue_dx<F>(TXB, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
             commit(&bar_a);
             issue_dw<F>(acc_addr(l - 1), dzb, aRing + slot(pa, l - 1), accum);
             if (l == NH) issue_dw<16>(acc_addr(NH + 1), aRing + slot(pa, NH), aDY, accum);
@@ -602,6 +639,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
             if (elect_one()) {
               const int pb = kB & 1;
               if (ib == 0) layer0(TZF, pb);
+              else if (ts) issue_forward_ts<F>(TZF, TAF, aW + (uint32_t)(ib - 1) * F * F * 2);
               else issue_forward<F>(TZF, aRing + slot(pb, ib - 1), aW + (uint32_t)(ib - 1) * F * F * 2);
               commit(&bar_b);
             }
@@ -689,7 +727,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           float* vc = v[c & 1];
 #pragma unroll
           for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
-          store_chunk16(dst, r, c_base + c, vc);
+          store_chunk16_both<false>(dst, r, c_base + c, vc, ts && st < NH, my_af + 8 * c);
           if (st == NH) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -747,7 +785,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
             vc[i] = dys * w4.x * fast_cos(vc[i]); vc[i + 1] = dys * w4.y * fast_cos(vc[i + 1]);
             vc[i + 2] = dys * w4.z * fast_cos(vc[i + 2]); vc[i + 3] = dys * w4.w * fast_cos(vc[i + 3]);
           }
-          store_chunk16_sat(dzb, r, c_base + c, vc);
+          store_chunk16_both<true>(dzb, r, c_base + c, vc, ts, my_ad + 8 * c);
         }
       }
       signal(&bar_lb);  // the "loss done" event
@@ -787,7 +825,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           const float* x = vx[c & 1];
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
-          store_chunk16_sat(dzb, r, c_base + c, z);
+          store_chunk16_both<true>(dzb, r, c_base + c, z, ts && l >= 2, my_ad + 8 * c);
         }
         TT(a2);
         signal(&bar_ra);
