@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 #ifdef BRIEF_TC_TIMING
   const int tslot = warp == 0 ? 0 : warp == GW ? 16 : warp == NW ? 32 : warp == NW + 1 ? 48 : -1;
 #endif
+  TT(k_start);
   const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
   const int net_id = a.work_net[wi];
   const int slice = blockIdx.x - a.work_prefix[wi];
@@ -573,6 +574,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   };
 
   mbar_wait(&bar_w, 0);
+  { TT(k_roles); TACC(9, k_roles - k_start); }
   if (mma_warp) {
     // ============================================ MMA-issue warp ===============================================
     // B events per tile, in order: NH+1 forward batches (0 = layer 0), then the "loss done" signal that arms the
@@ -836,7 +838,10 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     }
     { TT(a_end); TACC(7, a_end - a_start); TACC(8, n_tiles); }
   }
+  TT(k_sync0);
   __syncthreads();
+  TT(k_sync1);
+  TACC(10, k_sync1 - k_sync0);
 
   // ---- slice epilogue: loss partial + gradient partials (TMEM -> global), scale removed in fp32
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
@@ -897,6 +902,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   }
   tc_fence_before();
   __syncthreads();
+  { TT(k_end); TACC(11, k_end - k_sync1); TACC(12, k_end - k_start); }
   if (warp == 0) tmem_dealloc(tm, tcols);
 }
 

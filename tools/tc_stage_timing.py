@@ -43,6 +43,8 @@ show("group B (forward) warp 0", 0, ["wait f2 (tile k-2 done)", "wait sampler", 
                                     "y exchange + loss", "wait f1 (dz buffer free)", "dz_NH + signal", "TOTAL"], tb)
 ta = max(1, v[16 + 8])
 show("group A (backward) warp 0", 16, ["wait MMA (first stage of tile)", f"wait MMA x{NH - 1}", f"cos epilogue x{NH}", f"signal x{NH}", "", "", "", "TOTAL"], ta)
+print(f"per launch (warp 0): prologue {v[9] / n_runs:.0f} cyc, wait for the other roles at the end {v[10] / n_runs:.0f}, "
+      f"gradient flush {v[11] / n_runs:.0f}, kernel total {v[12] / n_runs:.0f}")
 tm = max(1, v[32 + 6])
 print(f"MMA warp: cycles per tile: A batches {v[32] / tm:.1f} ({v[33] / tm:.1f} batches), B batches/events {v[34] / tm:.1f} ({v[35] / tm:.1f}), "
       f"idle polls {v[36] / tm:.1f}, TOTAL {v[37] / tm:.1f}")
