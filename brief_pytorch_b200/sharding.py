@@ -96,14 +96,19 @@ def gather_blocks(local: Dict[int, torch.Tensor], owner: Sequence[int], shapes: 
             if rank == dst:
                 out[b] = local[b]
             continue
+        # payloads travel as raw bytes: NCCL has no 16-bit integer type (uint16 volumes are held as int16 bit patterns)
         if rank == r:
-            t = local[b].contiguous()
+            t = local[b].contiguous().view(torch.uint8)
             keep.append(t)
             ops.append(dist.P2POp(dist.isend, t, dst, group=group))
         elif rank == dst:
             dev = ref.device if ref is not None else ("cuda" if torch.cuda.is_available() else "cpu")
-            t = torch.empty(tuple(int(x) for x in shapes[b]), dtype=dtype, device=dev)
-            out[b] = t
+            shape = tuple(int(x) for x in shapes[b])
+            n_bytes = int(torch.empty((), dtype=dtype).element_size())
+            for x in shape:
+                n_bytes *= x
+            t = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
+            out[b] = t.view(dtype).reshape(shape)
             ops.append(dist.P2POp(dist.irecv, t, r, group=group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
