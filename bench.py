@@ -391,6 +391,23 @@ def main():
     torch.cuda.synchronize()
     t_dec_e2e = time.perf_counter() - t0
 
+    # ---- data prologue (HBM-bound): min / max / sum / sum^2 of raw voxels, one launch (brief_block_stats) ----
+    from brief_pytorch_b200.group import block_stats
+    big = torch.empty(1 << 30, dtype=torch.int16, device=dev)  # 2 GiB of uint16 voxels: 16x the L2
+    big.random_(0, 30000)
+    block_stats([big], "uint16")
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_stats = 0.0
+    for _ in range(5):
+        s0.record()
+        block_stats([big], "uint16")
+        s1.record()
+        torch.cuda.synchronize()
+        t_stats += s0.elapsed_time(s1) / 1e3
+    t_stats /= 5
+    stats_gbs = big.numel() * 2 / t_stats / 1e9
+    del big
+
     # ---- NCCL, after the hot path: decoded blocks -> rank 0 (variable-size send/recv), checked by a checksum table ----
     gather = None
     if world > 1:
@@ -455,6 +472,9 @@ def main():
                            "tensor_frac": vox_total / world * fwd_flops / t_dec / 1e12 / peak_tf},
             "final_loss_mean": float(table.mean()), "clocks": clk,
         }
+        line["block_stats"] = {"gbs": stats_gbs, "hbm_frac": stats_gbs / pk["hbm_gbs"], "bytes": 2 << 30,
+                               "note": "min/max/sum/sum^2 of a 2 GiB uint16 buffer, one launch incl. its 2 tiny copies; "
+                                       "rank 0's figure; peak = " + pk["src"] + " copy bandwidth (read+write)"}
         if gather is not None:
             line["gather_decoded_blocks"] = gather
         if world == 1 and not args.no_cpu_baseline:

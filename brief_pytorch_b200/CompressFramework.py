@@ -22,7 +22,7 @@ import torch
 import yaml
 
 from . import misc, sharding
-from .group import NetSpec, SirenGroup, pack_module_params, unpack_module_params
+from .group import NetSpec, SirenGroup, block_stats, pack_module_params, unpack_module_params
 from .io import get_type_max
 from .ModelSave import load_model, save_model
 from .Networks import ALL_CALC_PHI_FEATURES, ALL_CALC_PHI_PARAM_COUNT, get_nnmodule_param_count, init_phi
@@ -134,15 +134,21 @@ class NFGR:
             specs.append(NetSpec(b.features, kw["layers"], kw["w0"], b.shape, kw["coords_channel"], kw["data_channel"]))
         grp = SirenGroup(specs, self.device, self.precision)
         self._keep = []
+        # raw blocks go to the device in their own dtype; min / max of every block in ONE launch (brief_block_stats)
+        # instead of normalize_data's host numpy passes (utils/io.py:67-80)
+        raws = [np.ascontiguousarray(b.data[..., 0]) for b in blocks]
+        if len({r.dtype for r in raws}) != 1:
+            raise NotImplementedError("blocks of one volume share a dtype")
+        dev_raw = [torch.from_numpy(r.view(np.int16) if r.dtype == np.uint16 else r).to(grp.device) for r in raws]
+        stats = block_stats(dev_raw, raws[0].dtype.name)
         for i, b in enumerate(blocks):
             grp.set_axes(i, str(C["coords_mode"]))
             grp.load_module(i, b.module)
-            raw = np.ascontiguousarray(b.data[..., 0])
-            x32 = raw.astype(np.float32)
-            vmin, vmax = float(x32.min()), float(x32.max())
+            raw = raws[i]
+            vmin, vmax = float(stats[i, 0]), float(stats[i, 1])
             b.sideinfos = {"dtype": raw.dtype.name, "min": vmin, "max": vmax, "data_shape": list(b.data.shape),
                            "phi_features": int(b.features), "phi_name": self.opt["Module"]["phi"]["name"]}
-            t = torch.from_numpy(raw.view(np.int16) if raw.dtype == np.uint16 else raw).to(grp.device)
+            t = dev_raw[i]
             rules = misc.weight_rules_for_kernel(raw, C["loss"]["weight"])
             weight = None
             if rules is None:  # 'exp' rule or more than 4 rules: explicit per-voxel weights

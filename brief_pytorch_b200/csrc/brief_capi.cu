@@ -716,8 +716,8 @@ int brief_fit_run(BriefGroup* g, const BriefOptConfig* cfg, uint64_t seed, int64
 int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n, float* dev_out, float* dev_layers,
                   void* stream) {
   RC(check_net(g, net));
+  if (n == 0) return 0;  // zero coordinates: nothing to do (empty tensors have null pointers)
   if (!dev_coords || !dev_out || n < 0) return fail(BRIEF_ERR_INVALID, "brief_forward: bad arguments");
-  if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   RC(use_device(g));
   RC(sync_nets(g, st));
@@ -800,6 +800,55 @@ int brief_gather(BriefGroup* g, int32_t net, const int64_t* dev_idx, int64_t bat
   RC(sync_nets(g, st));
   LAUNCH(launch_gather(g->d_nets.p, net, g->d_axes.p, reinterpret_cast<const long long*>(dev_idx), batch, dev_coords,
                        dev_data, dev_weight, st));
+  return 0;
+}
+
+int brief_block_stats(void* const* host_dev_raw, const int64_t* host_sizes, int32_t n_blocks, int32_t dtype,
+                      int32_t device, double* host_out, void* stream) {
+  if (!host_dev_raw || !host_sizes || !host_out || n_blocks < 0) return fail(BRIEF_ERR_INVALID, "brief_block_stats: bad arguments");
+  if (dtype < 0 || dtype > 2) return fail(BRIEF_ERR_INVALID, "unknown dtype %d", dtype);
+  if (n_blocks == 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(BRIEF_ERR_CUDA, "CUDA device %d not available", device);
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  long long max_size = 0;
+  for (int i = 0; i < n_blocks; ++i) {
+    if (!host_dev_raw[i] || host_sizes[i] < 0) return fail(BRIEF_ERR_INVALID, "block %d: null pointer or negative size", i);
+    max_size = std::max<long long>(max_size, host_sizes[i]);
+  }
+  // one device scratch: [pointers | sizes | ord(min), ord(max) | sum, sumsq]
+  const size_t nb = (size_t)n_blocks;
+  const size_t off_sizes = nb * sizeof(void*), off_ord = off_sizes + nb * sizeof(long long);
+  const size_t off_sum = (off_ord + nb * 2 * sizeof(unsigned int) + 7) & ~(size_t)7, total = off_sum + nb * 2 * sizeof(double);
+  std::vector<unsigned char> h(total, 0);
+  memcpy(h.data(), host_dev_raw, nb * sizeof(void*));
+  for (size_t i = 0; i < nb; ++i) {
+    reinterpret_cast<long long*>(h.data() + off_sizes)[i] = host_sizes[i];
+    reinterpret_cast<unsigned int*>(h.data() + off_ord)[2 * i] = 0xffffffffu;  // ord(min) starts at the top
+  }
+  unsigned char* d = nullptr;
+  CU(cudaMalloc(&d, total));
+  cudaError_t e = cudaMemcpyAsync(d, h.data(), total, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = launch_block_stats(reinterpret_cast<void* const*>(d), reinterpret_cast<const long long*>(d + off_sizes), n_blocks,
+                           max_size, dtype, reinterpret_cast<unsigned int*>(d + off_ord), reinterpret_cast<double*>(d + off_sum),
+                           sms, st);
+  if (e == cudaSuccess) { g_launches.fetch_add(1); e = cudaMemcpyAsync(h.data(), d, total, cudaMemcpyDeviceToHost, st); }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "brief_block_stats: %s", cudaGetErrorString(e));
+  for (size_t i = 0; i < nb; ++i) {
+    const unsigned int* o = reinterpret_cast<const unsigned int*>(h.data() + off_ord) + 2 * i;
+    const double* s2 = reinterpret_cast<const double*>(h.data() + off_sum) + 2 * i;
+    host_out[4 * i + 0] = host_sizes[i] ? (double)stats_ord_to_float(o[0]) : 0.0;
+    host_out[4 * i + 1] = host_sizes[i] ? (double)stats_ord_to_float(o[1]) : 0.0;
+    host_out[4 * i + 2] = s2[0];
+    host_out[4 * i + 3] = s2[1];
+  }
   return 0;
 }
 

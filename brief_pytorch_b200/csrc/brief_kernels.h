@@ -83,6 +83,11 @@ cudaError_t launch_gather(const NetDev* nets, int net_id, const float* axes, con
 cudaError_t launch_sample_indices(uint64_t seed, uint64_t step, uint32_t net, long long batch, long long pop,
                                   long long* out, cudaStream_t st);
 
+// brief_data.cu
+cudaError_t launch_block_stats(const void* const* dev_ptrs, const long long* dev_sizes, int n_blocks, long long max_size,
+                               int dtype, unsigned int* stat_ord, double* stat_sum, int num_sms, cudaStream_t st);
+float stats_ord_to_float(unsigned int o);
+
 // brief_opt.cu
 cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st);
 cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, unsigned char* wpack, cudaStream_t st);

@@ -274,6 +274,27 @@ def sample_indices(seed: int, step: int, net: int, batch: int, pop: int, device=
     return out
 
 
+def block_stats(blocks: Sequence[torch.Tensor], np_dtype: Optional[str] = None) -> np.ndarray:
+    """min, max, sum, sum of squares of every raw block (CUDA tensors, contiguous) in one launch -> float64 [n, 4].
+    Replaces the host numpy passes of normalize_data / alloc_param (utils/io.py:67-80, utils/misc.py:402-422)."""
+    lib = _cabi.load()
+    if not blocks:
+        return np.zeros((0, 4))
+    dev = blocks[0].device
+    if np_dtype is None:
+        np_dtype = {torch.uint8: "uint8", torch.int16: "uint16", torch.float32: "float32"}[blocks[0].dtype]
+    for t in blocks:
+        assert t.is_cuda and t.is_contiguous() and t.device == dev and t.dtype == blocks[0].dtype
+    n = len(blocks)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in blocks])
+    sizes = (C.c_int64 * n)(*[t.numel() for t in blocks])
+    out = np.zeros((n, 4), dtype=np.float64)
+    with torch.cuda.device(dev):
+        check(lib.brief_block_stats(ptrs, sizes, n, _NP2DT[np_dtype], dev.index if dev.index is not None else 0,
+                                    out.ctypes.data_as(C.POINTER(C.c_double)), _stream(dev)))
+    return out
+
+
 def launch_count() -> int:
     return int(_cabi.load().brief_launch_count())
 

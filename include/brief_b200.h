@@ -186,6 +186,14 @@ int brief_gather(BriefGroup* g, int32_t net, const int64_t* dev_idx, int64_t bat
 int brief_sample_indices(uint64_t seed, uint64_t step, int32_t net, int64_t batch, int64_t pop,
                          int64_t* dev_out, void* stream);
 
+/* Replaces the host numpy passes of normalize_data's data.min() / data.max() (utils/io.py:67-80) and the per-chunk
+ * variance of alloc_param 'by_var' (utils/misc.py:402-422) for n_blocks contiguous raw blocks in ONE launch:
+ * host_dev_raw[i] = device pointer of block i (dtype as in brief_group_bind_volume), host_sizes[i] = its element
+ * count.  host_out receives 4 doubles per block: min, max (exact values of the raw dtype), sum, sum of squares
+ * (accumulated in fp64).  Synchronises `stream`. */
+int brief_block_stats(void* const* host_dev_raw, const int64_t* host_sizes, int32_t n_blocks, int32_t dtype,
+                      int32_t device, double* host_out, void* stream);
+
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
 int64_t brief_launch_count(void);
 void brief_reset_launch_count(void);
