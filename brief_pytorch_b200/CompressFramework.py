@@ -61,10 +61,14 @@ class Block:
 
 
 class NFGR:
-    def __init__(self, opt: dict, device: int | str = 0, precision: str = "auto"):
+    def __init__(self, opt: dict, device: int | str = 0, precision: str = "auto", reproducible: bool = False):
+        """reproducible=True: a block's fitted parameters are bit-identical whichever rank owns it and whatever else
+        shares its GPU (per-network slicing, SirenGroup.set_slicing); the default slicing is faster and reproducible
+        run to run for a fixed sharding, but may differ in the last bits between shardings."""
         self.opt = copy.deepcopy(opt)
         self.device = device
         self.precision = precision
+        self.reproducible = reproducible
         if self.opt["Compress"].get("half", False):
             raise NotImplementedError("Compress.half is not part of the fused SIREN path")
         if self.opt["Compress"]["loss"]["name"] != "datal2":
@@ -114,7 +118,8 @@ class NFGR:
 
     # ---- fit (main.py:322-454 for every block at once) -----------------------------------------------------------
     def fit_blocks(self, blocks: Sequence[Block], max_steps: Optional[int] = None, seed: int = 42,
-                   sampler_generator: str = "device", on_checkpoint=None) -> SirenGroup:
+                   sampler_generator: str = "device", on_checkpoint=None,
+                   stream_ids: Optional[Sequence[int]] = None) -> SirenGroup:
         """Fit every block's network (grouped launches).  Initial weights are drawn block by block from torch's CPU
         generator in the reference's order (seed -> init_phi).  Returns the live group (parameters on the device);
         block.module / block.sideinfos / block.loss are filled in."""
@@ -133,6 +138,10 @@ class NFGR:
             assert get_nnmodule_param_count(b.module) == want  # main.py:261-262
             specs.append(NetSpec(b.features, kw["layers"], kw["w0"], b.shape, kw["coords_channel"], kw["data_channel"]))
         grp = SirenGroup(specs, self.device, self.precision)
+        grp.set_slicing(self.reproducible)
+        if stream_ids is not None:  # global block indices: a block draws the same samples whichever rank owns it
+            for i, sid in enumerate(stream_ids):
+                grp.set_stream(i, sid)
         self._keep = []
         # raw blocks go to the device in their own dtype; min / max of every block in ONE launch (brief_block_stats)
         # instead of normalize_data's host numpy passes (utils/io.py:67-80)
@@ -279,7 +288,7 @@ class NFGR:
         owner = sharding.lpt_assign(costs, world)
         mine = sharding.my_blocks(owner, rank)
         if mine:
-            self.fit_blocks([blocks[i] for i in mine], steps, seed).close()
+            self.fit_blocks([blocks[i] for i in mine], steps, seed, stream_ids=mine).close()
         if compressed_dir is not None:
             self.save_compressed([blocks[i] for i in mine], data.shape, compressed_dir)
         return blocks, mine

@@ -59,6 +59,8 @@ PROTOTYPES = {
     "brief_group_bind_volume": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_f32, c_f32, c_vp,
                                         C.POINTER(WeightRule), c_i32, c_f32]),
     "brief_group_set_sampler": (c_i32, [c_vp, c_i32, c_i32, c_i32]),
+    "brief_group_set_stream": (c_i32, [c_vp, c_i32, C.c_uint32]),
+    "brief_group_set_slicing": (c_i32, [c_vp, c_i32]),
     "brief_fit_step": (c_i32, [c_vp, c_vp, c_u64, c_u64, c_vp, c_vp]),
     "brief_fit_kernels": (c_i32, [c_vp, c_vp, c_u64, c_u64, c_vp]),
     "brief_opt_step": (c_i32, [c_vp, c_i32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp]),

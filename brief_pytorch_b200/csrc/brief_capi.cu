@@ -102,6 +102,7 @@ struct BriefGroup {
   DevBuf<void*> d_outptrs;
   bool nets_dirty = true;   // host NetDev array differs from the device copy
   bool work_dirty = true;   // sampler changed: rebuild the fit decomposition
+  int slicing = 0;          // BriefSlicing
   bool wpack_dirty = true;  // params changed since the fp16 operand image was packed
   bool any_tc = false, any_simt = false;
   // fit
@@ -280,7 +281,14 @@ int finalize(BriefGroup* g, cudaStream_t st) {
     const long long n_tiles = ((long long)n.batch + tile - 1) / tile;
     const long long max_slices = std::max<long long>(1, (long long)(kPartialCapBytes / ((size_t)n.P_dev * 4)));
     long long tps = (n_tiles + max_slices - 1) / max_slices;
-    if (tc) tps = std::max<long long>(tps, tc_tps[n.F_PAD / 16]);
+    if (tc) {
+      // PER_NETWORK: the network fills one wave by itself, so its slice boundaries (and with them the fp32
+      // summation order of its gradients) do not depend on what else shares the GPU
+      const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(n.F_PAD, g->tc_L[n.F_PAD / 16]);
+      const long long own = g->slicing == BRIEF_SLICING_PER_NETWORK ? std::max<long long>(1, (n_tiles + wave - 1) / wave)
+                                                                    : tc_tps[n.F_PAD / 16];
+      tps = std::max<long long>(tps, own);
+    }
     tps = std::max<long long>(tps, 1);
     n.slice_len = (int)(tps * tile);
     n.n_slices = (int)((n_tiles + tps - 1) / tps);
@@ -492,6 +500,7 @@ int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device
     n.lo = 0.f; n.hi = 100.f; n.vmin = 0.f; n.vmax = 1.f;
     n.dn_lo = 0.f; n.dn_hi = 100.f; n.dn_vmin = 0.f; n.dn_vmax = 1.f; n.dn_range = 1.f;
     // main.py:332-334: whole-block sampling only for blocks of at most 80^3 voxels
+    n.stream_id = (unsigned int)i;
     n.mode = n.n_vox <= 80LL * 80 * 80 ? BRIEF_SAMPLE_FULL_BLOCK : BRIEF_SAMPLE_RANDOM_POINTS;
     n.batch = n.mode == BRIEF_SAMPLE_FULL_BLOCK ? (int)n.n_vox : 100000;
     g->nets[i] = n;
@@ -654,6 +663,21 @@ int brief_group_set_sampler(BriefGroup* g, int32_t net, int32_t mode, int32_t ba
   n.batch = mode == BRIEF_SAMPLE_FULL_BLOCK ? (int)std::min<long long>(n.n_vox, 0x7fffffffLL) : batch;
   g->work_dirty = true;
   g->nets_dirty = true;
+  return 0;
+}
+
+int brief_group_set_stream(BriefGroup* g, int32_t net, uint32_t stream_id) {
+  RC(check_net(g, net));
+  g->nets[net].stream_id = stream_id;
+  g->nets_dirty = true;
+  return 0;
+}
+
+int brief_group_set_slicing(BriefGroup* g, int32_t mode) {
+  if (!g) return fail(BRIEF_ERR_INVALID, "null group");
+  if (mode != BRIEF_SLICING_FILL_WAVE && mode != BRIEF_SLICING_PER_NETWORK) return fail(BRIEF_ERR_INVALID, "unknown slicing mode %d", mode);
+  g->slicing = mode;
+  g->work_dirty = true;
   return 0;
 }
 

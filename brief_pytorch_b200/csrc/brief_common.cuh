@@ -49,6 +49,7 @@ struct NetDev {
   int mode;                    // BriefSamplerMode
   int batch;                   // samples per step (== n_vox for FULL_BLOCK)
   long long idx_off;           // offset into the replay index array
+  unsigned int stream_id;      // key of this network's on-device sampler stream (default: its index in the group)
   // work decomposition for fit
   int slice_len;               // samples per slice
   int n_slices;

@@ -192,6 +192,14 @@ class SirenGroup:
         m = {"randomcube": SAMPLE_FULL_BLOCK, "full": SAMPLE_FULL_BLOCK, "randompoint": SAMPLE_RANDOM_POINTS}[mode]
         check(self._lib.brief_group_set_sampler(self._h, net, m, int(batch)))
 
+    def set_stream(self, net: int, stream_id: int) -> None:
+        """Key of the network's on-device sampler stream (pass the block's global index when blocks are sharded)."""
+        check(self._lib.brief_group_set_stream(self._h, net, int(stream_id)))
+
+    def set_slicing(self, per_network: bool) -> None:
+        """per_network=True: every network's result is bit-identical whatever else shares the GPU (slower)."""
+        check(self._lib.brief_group_set_slicing(self._h, 1 if per_network else 0))
+
     # ---- hot path -----------------------------------------------------------------------------------------
     def fit_step(self, idx: Optional[torch.Tensor] = None, seed: int = 0, step: int = 0) -> torch.Tensor:
         """gather + forward + weighted L2 + backward for every network; returns the per-network loss."""

@@ -140,6 +140,19 @@ int brief_group_bind_volume(BriefGroup* g, int32_t net, const void* dev_raw, int
 /* Sampler of main.py:367-371 for this network. `batch` is ignored for FULL_BLOCK (= voxel count). */
 int brief_group_set_sampler(BriefGroup* g, int32_t net, int32_t mode, int32_t batch);
 
+/* Key of the network's on-device sampler stream (Philox counter word).  Default: the network's index in the group;
+ * a caller that shards blocks over ranks passes the block's GLOBAL index so that a block draws the same samples
+ * whichever rank owns it. */
+int brief_group_set_stream(BriefGroup* g, int32_t net, uint32_t stream_id);
+
+/* How a network's step batch is cut into per-CTA slices (each slice accumulates its gradient in TMEM, the optimiser
+ * kernel adds the slices in order).  FILL_WAVE (default, fastest): slices sized so that ALL networks of a width
+ * bucket together fill one wave of CTAs.  PER_NETWORK: a network's slices depend only on its own batch and the
+ * device, so its fp32 summation order — and therefore every bit of its result — is independent of what else shares
+ * the GPU (the 1/2/4/8-GPU equality of SURVEY.md 8e); costs extra waves when many networks share a GPU. */
+typedef enum BriefSlicing { BRIEF_SLICING_FILL_WAVE = 0, BRIEF_SLICING_PER_NETWORK = 1 } BriefSlicing;
+int brief_group_set_slicing(BriefGroup* g, int32_t mode);
+
 /* ---- hot path ----------------------------------------------------------------------------------- */
 /* One training step for EVERY network of the group: sampler gather + forward + weighted L2
  * (datal2, main.py:176-182) + backward (main.py:385-396).  Gradients stay on the device.
