@@ -192,8 +192,8 @@ def run_reference(args, plan):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vessel", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "fp32"])
@@ -203,7 +203,7 @@ def main():
     args.warmup = max(args.warmup, 3)
     plan = plan_blocks(args.workload)
     if args.impl == "reference":
-        if args.steps == 200 and args.warmup == 20:
+        if args.steps == 1000 and args.warmup == 50:
             args.steps, args.warmup = 20, 3
         return run_reference(args, plan)
 
