@@ -2,6 +2,8 @@
 // group bookkeeping: arenas, padded<->packed parameter conversion, work tables, launch sequencing.
 // No torch types cross this boundary; no CPU compute path exists behind it.
 #include <algorithm>
+#include <array>
+#include <set>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -824,6 +826,54 @@ int brief_gather(BriefGroup* g, int32_t net, const int64_t* dev_idx, int64_t bat
   RC(sync_nets(g, st));
   LAUNCH(launch_gather(g->d_nets.p, net, g->d_axes.p, reinterpret_cast<const long long*>(dev_idx), batch, dev_coords,
                        dev_data, dev_weight, st));
+  return 0;
+}
+
+int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width, const int32_t* host_blocks,
+                  int32_t n_blocks, int32_t index_a, int32_t index_b, int32_t thres, int32_t* host_masks, int32_t device,
+                  void* stream) {
+  if (!host_blocks || n_blocks < 0 || depth < 0 || height < 0 || width < 0)
+    return fail(BRIEF_ERR_INVALID, "brief_deblock: bad arguments");
+  // seam list (deblock.cpp:244-276): a block lists its left / right / down / up seam for every z of its range unless
+  // the seam's flag is up; a flag goes up when the block's seam at z1 is already listed and never comes down again
+  std::vector<DeblockBlock> blocks((size_t)n_blocks);
+  std::set<std::array<int, 5>> seen;
+  bool flags[4] = {false, false, false, false};
+  for (int i = 0; i < n_blocks; ++i) {
+    const int32_t* b = host_blocks + 6 * (size_t)i;
+    DeblockBlock k{b[0], b[1], b[2], b[3], b[4], b[5], 0};
+    if (k.z1 < 0 || k.z2 < k.z1 || k.y1 < 0 || k.y2 < k.y1 || k.x1 < 0 || k.x2 < k.x1 ||
+        (dev_volume && (k.z2 >= depth || k.y2 >= height || k.x2 >= width)))
+      return fail(BRIEF_ERR_INVALID, "brief_deblock: block %d out of range", i);
+    const int cand[4][4] = {{k.x1, k.x1, k.y1, k.y2}, {k.x2, k.x2, k.y1, k.y2}, {k.x1, k.x2, k.y1, k.y1}, {k.x1, k.x2, k.y2, k.y2}};
+    for (int s = 0; s < 4; ++s)
+      if (seen.count({k.z1, cand[s][0], cand[s][1], cand[s][2], cand[s][3]})) flags[s] = true;
+    for (int s = 0; s < 4; ++s) {
+      if (flags[s]) continue;
+      k.mask |= 1 << s;
+      for (int z = k.z1; z <= k.z2; ++z) seen.insert({z, cand[s][0], cand[s][1], cand[s][2], cand[s][3]});
+    }
+    blocks[(size_t)i] = k;
+    if (host_masks) host_masks[i] = k.mask;
+  }
+  if (!dev_volume || n_blocks == 0 || depth == 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(BRIEF_ERR_CUDA, "CUDA device %d not available", device);
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  // thresholds exactly as the reference forms them (deblock.cpp:13-21): double arithmetic, float result
+  const float xa = (float)index_a;
+  const float alpha = (float)(0.8 * (std::pow(2.0, (double)(xa / 6)) - 1));
+  const float beta = (float)(0.5 * (double)(float)index_b - 7);
+  DeblockBlock* d = nullptr;
+  CU(cudaMalloc(&d, blocks.size() * sizeof(DeblockBlock)));
+  cudaError_t e = cudaMemcpyAsync(d, blocks.data(), blocks.size() * sizeof(DeblockBlock), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = launch_deblock(reinterpret_cast<unsigned short*>(dev_volume), depth, height, width, d, n_blocks, alpha, beta, thres, st);
+  if (e == cudaSuccess) { g_launches.fetch_add(1); e = cudaStreamSynchronize(st); }
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "brief_deblock: %s", cudaGetErrorString(e));
   return 0;
 }
 

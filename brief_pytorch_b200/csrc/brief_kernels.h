@@ -88,6 +88,11 @@ cudaError_t launch_block_stats(const void* const* dev_ptrs, const long long* dev
                                int dtype, unsigned int* stat_ord, double* stat_sum, int num_sms, cudaStream_t st);
 float stats_ord_to_float(unsigned int o);
 
+// brief_deblock.cu
+struct DeblockBlock { int z1, z2, y1, y2, x1, x2, mask; };  // inclusive ends; mask bit 0..3 = left, right, down, up seam listed
+cudaError_t launch_deblock(unsigned short* img, int D, int H, int W, const DeblockBlock* dev_blocks, int n_blocks,
+                           float alpha, float beta, int thres, cudaStream_t st);
+
 // brief_opt.cu
 cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st);
 cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, unsigned char* wpack, cudaStream_t st);

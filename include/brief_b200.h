@@ -207,6 +207,18 @@ int brief_sample_indices(uint64_t seed, uint64_t step, int32_t net, int64_t batc
 int brief_block_stats(void* const* host_dev_raw, const int64_t* host_sizes, int32_t n_blocks, int32_t dtype,
                       int32_t device, double* host_out, void* stream);
 
+/* Replaces the reference's deblocking post-filter (deblock.cpp:226-321, its only native component; deblock.py is the
+ * float twin) on a decoded uint16 volume [depth][height][width] in device memory, in place, bit for bit:
+ * host_blocks holds n_blocks x 6 int32 (z1, z2, y1, y2, x1, x2, inclusive ends — the chunk directory names
+ * d_z1_z2-h_y1_y2-w_x1_x2 of compressed/module) IN THE ORDER the reference's readdir() loop lists them: seams are
+ * filtered sequentially in place, so the order is part of the result.  index_a / index_b / thres: deblock.cpp:326
+ * (51, 2000, 65535).  host_masks (optional, n_blocks int32): receives the seam mask per block (bit 0..3 = left, right,
+ * down, up seam listed; the reference's sticky duplicate flags, deblock.cpp:244-276).  With dev_volume == NULL only the
+ * masks are computed (no CUDA call). */
+int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width, const int32_t* host_blocks,
+                  int32_t n_blocks, int32_t index_a, int32_t index_b, int32_t thres, int32_t* host_masks, int32_t device,
+                  void* stream);
+
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
 int64_t brief_launch_count(void);
 void brief_reset_launch_count(void);
