@@ -136,6 +136,14 @@ class NFGR:
             b.module = init_phi(kw)
             want = ALL_CALC_PHI_PARAM_COUNT[kw["name"]](**{k: v for k, v in kw.items() if k != "name"})
             assert get_nnmodule_param_count(b.module) == want  # main.py:261-262
+            init_path = str(C["param"].get("init_net_path", "none"))
+            if init_path != "none":  # warm start (main.py:349-354): weights only, no optimiser state
+                if len(blocks) == 1:
+                    load_model(b.module, init_path)
+                elif os.path.isdir(os.path.join(init_path, b.name, "module")):  # a compressed/module tree of a divided run
+                    load_model(b.module, os.path.join(init_path, b.name, "module"))
+                else:
+                    raise FileNotFoundError(f"init_net_path has no module for block {b.name}")
             specs.append(NetSpec(b.features, kw["layers"], kw["w0"], b.shape, kw["coords_channel"], kw["data_channel"]))
         grp = SirenGroup(specs, self.device, self.precision)
         grp.set_slicing(self.reproducible)

@@ -877,6 +877,38 @@ int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width
   return 0;
 }
 
+int brief_volume_quality(const void* dev_a, const void* dev_b, int32_t dtype, int32_t depth, int32_t height, int32_t width,
+                         double data_range, double* host_out, int32_t device, void* stream) {
+  if (!dev_a || !dev_b || !host_out || depth < 1) return fail(BRIEF_ERR_INVALID, "brief_volume_quality: bad arguments");
+  if (dtype < 0 || dtype > 2) return fail(BRIEF_ERR_INVALID, "unknown dtype %d", dtype);
+  if (height < 11 || width < 11)
+    return fail(BRIEF_ERR_UNSUPPORTED, "brief_volume_quality: slices of %dx%d are smaller than the 11-tap window", height, width);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(BRIEF_ERR_CUDA, "CUDA device %d not available", device);
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  // _fspecial_gauss_1d(11, 1.5), utils/ssim.py:9-24: fp32 exp, normalised by the fp32 sum
+  float win[11], sum = 0.f;
+  for (int k = 0; k < 11; ++k) {
+    const float c = (float)(k - 5);
+    win[k] = expf(-(c * c) / (2.f * 1.5f * 1.5f));
+    sum += win[k];
+  }
+  for (int k = 0; k < 11; ++k) win[k] /= sum;
+  const float c1 = (float)((0.01 * data_range) * (0.01 * data_range)), c2 = (float)((0.03 * data_range) * (0.03 * data_range));
+  double* d = nullptr;
+  CU(cudaMalloc(&d, 2 * sizeof(double)));
+  cudaError_t e = cudaMemsetAsync(d, 0, 2 * sizeof(double), st);
+  if (e == cudaSuccess) e = launch_quality(dev_a, dev_b, dtype, depth, height, width, win, c1, c2, d, st);
+  if (e == cudaSuccess) { g_launches.fetch_add(1); e = cudaMemcpyAsync(host_out, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, st); }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "brief_volume_quality: %s", cudaGetErrorString(e));
+  host_out[2] = (double)depth * (double)(height - 10) * (double)(width - 10);
+  return 0;
+}
+
 int brief_block_stats(void* const* host_dev_raw, const int64_t* host_sizes, int32_t n_blocks, int32_t dtype,
                       int32_t device, double* host_out, void* stream) {
   if (!host_dev_raw || !host_sizes || !host_out || n_blocks < 0) return fail(BRIEF_ERR_INVALID, "brief_block_stats: bad arguments");

@@ -93,6 +93,10 @@ struct DeblockBlock { int z1, z2, y1, y2, x1, x2, mask; };  // inclusive ends; m
 cudaError_t launch_deblock(unsigned short* img, int D, int H, int W, const DeblockBlock* dev_blocks, int n_blocks,
                            float alpha, float beta, int thres, cudaStream_t st);
 
+// brief_quality.cu
+cudaError_t launch_quality(const void* a, const void* b, int dtype, int D, int H, int W, const float* win11, float c1, float c2,
+                           double* dev_out, cudaStream_t st);
+
 // brief_opt.cu
 cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st);
 cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, unsigned char* wpack, cudaStream_t st);

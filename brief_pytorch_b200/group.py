@@ -303,6 +303,24 @@ def block_stats(blocks: Sequence[torch.Tensor], np_dtype: Optional[str] = None) 
     return out
 
 
+def volume_quality(a: torch.Tensor, b: torch.Tensor, data_range: float, np_dtype: Optional[str] = None) -> dict:
+    """mse / psnr / ssim of two CUDA volumes [D,H,W] (same dtype) in one launch — eval_performance (utils/misc.py:477-499)
+    with the reference's SSIM (utils/ssim.py).  uint16 volumes may be held as int16 bit patterns."""
+    lib = _cabi.load()
+    assert a.is_cuda and b.is_cuda and a.shape == b.shape and a.dtype == b.dtype and a.dim() == 3
+    a, b = a.contiguous(), b.contiguous()
+    if np_dtype is None:
+        np_dtype = {torch.uint8: "uint8", torch.int16: "uint16", torch.float32: "float32"}[a.dtype]
+    out = (C.c_double * 3)()
+    d, h, w = (int(x) for x in a.shape)
+    with torch.cuda.device(a.device):
+        check(lib.brief_volume_quality(_ptr(a), _ptr(b), _NP2DT[np_dtype], d, h, w, float(data_range), out,
+                                       a.device.index or 0, _stream(a.device)))
+    mse = out[0] / (d * h * w)
+    return {"mse": mse, "psnr": float(-10.0 * np.log10(mse / (data_range * data_range))) if mse > 0 else float("inf"),
+            "ssim": out[1] / out[2]}
+
+
 def launch_count() -> int:
     return int(_cabi.load().brief_launch_count())
 

@@ -219,6 +219,16 @@ int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width
                   int32_t n_blocks, int32_t index_a, int32_t index_b, int32_t thres, int32_t* host_masks, int32_t device,
                   void* stream);
 
+/* Replaces eval_performance / cal_mse / cal_psnr / cal_ssim (utils/misc.py:447-499) and utils/ssim.py:9-150 for two
+ * volumes [depth][height][width] of the same dtype in device memory, in one pass: host_out[0] = sum of squared
+ * differences, host_out[1] = sum of the SSIM map (11-tap Gaussian window sigma 1.5, valid region, K = (0.01, 0.03),
+ * C1/C2 from data_range) over all valid pixels of all slices, host_out[2] = number of valid pixels
+ * (depth * (height-10) * (width-10)).  MSE = out[0] / voxels, PSNR = -10 log10(MSE / data_range^2),
+ * SSIM = out[1] / out[2] (all slices have the same valid area, so this is the reference's mean of slice means).
+ * height, width >= 11.  Synchronises `stream`. */
+int brief_volume_quality(const void* dev_a, const void* dev_b, int32_t dtype, int32_t depth, int32_t height, int32_t width,
+                         double data_range, double* host_out, int32_t device, void* stream);
+
 /* Kernel launches issued by this library since the last reset (bench.py's gpu_launches). */
 int64_t brief_launch_count(void);
 void brief_reset_launch_count(void);

@@ -161,3 +161,24 @@ def test_block_ownership_does_not_change_a_blocks_result(shape, steps):
     for i in range(4):
         np.testing.assert_array_equal(got[i], pack_module_params(all_blocks[i].module))
         assert np.isfinite(got[i]).all()
+
+
+@pytest.mark.gpu
+def test_warm_start_from_a_compressed_directory(tmp_path):
+    """Compress.param.init_net_path (main.py:345-354): a second run that starts from the first run's modules begins
+    at the first run's final loss instead of the initial one."""
+    from brief_pytorch_b200 import synth
+    from brief_pytorch_b200.CompressFramework import NFGR
+    o = opt()
+    o["Compress"]["divide"]["divide_type"] = "total_1_2_2"
+    o["Compress"]["param"]["filesize_ratio"] = 16
+    o["Compress"]["checkpoints"] = "none"
+    vol = synth.vessel((16, 48, 48), seed=7)
+    cdir = str(tmp_path / "compressed")
+    cold, _ = NFGR(o, 0, "f16").compress_divide(vol, cdir, max_steps=150)
+    first, _ = NFGR(o, 0, "f16").compress_divide(vol, None, max_steps=1)
+    o["Compress"]["param"]["init_net_path"] = os.path.join(cdir, "module")
+    warm, _ = NFGR(o, 0, "f16").compress_divide(vol, None, max_steps=1)
+    for c, f, w in zip(cold, first, warm):
+        assert w.loss < f.loss - 1.0                 # clearly below a cold first step ...
+        assert abs(w.loss - c.loss) < 0.01 * c.loss  # ... and where the first run stopped (one Adamax step apart)

@@ -187,3 +187,23 @@ def test_block_stats_kernel_is_exact(dtype):
         np.testing.assert_allclose(g[2], a64.sum(), rtol=1e-12, atol=1e-9)
         np.testing.assert_allclose(g[3], (a64 * a64).sum(), rtol=1e-12)
     assert block_stats([]).shape == (0, 4)
+
+
+@pytest.mark.parametrize("dtype,shape", [("uint16", (5, 37, 53)), ("uint8", (3, 64, 48)), ("uint16", (2, 11, 11))])
+def test_quality_kernel_matches_reference_metrics(dtype, shape):
+    """mse / psnr / ssim in one launch (brief_volume_quality) against the oracle's restatement of eval_performance
+    (utils/misc.py:447-499, utils/ssim.py): PSNR within 1e-3 dB, SSIM within 1e-4 (north-star bars: 0.1 dB / 0.002)."""
+    from brief_pytorch_b200 import misc
+    rng = np.random.default_rng(17)
+    top = 255 if dtype == "uint8" else 65535
+    zz, yy, xx = np.meshgrid(*[np.arange(n) for n in shape], indexing="ij")
+    a = (0.45 * top * (1 + np.sin(yy / 6.0 + zz) * np.cos(xx / 4.0)) + rng.integers(0, top // 50, size=shape))
+    a = np.clip(a, 0, top).astype(dtype)[..., None]
+    b = np.clip(a.astype(np.int64) + rng.integers(-top // 40, top // 40 + 1, size=a.shape), 0, top).astype(dtype)
+    got = misc.eval_performance(7, a, b, device="cuda")
+    a32, b32 = a.astype(np.float32), b.astype(np.float32)
+    assert abs(got["psnr"] - O.cal_psnr(a32, b32, top)) < 1e-3
+    assert abs(got["ssim"] - O.cal_ssim(a32, b32, top)) < 1e-4
+    np.testing.assert_allclose(got["mse"], ((a32.astype(np.float64) - b32) ** 2).mean(), rtol=1e-9)
+    same = misc.eval_performance(7, a, a, device="cuda")
+    assert same["mse"] == 0 and same["psnr"] == float("inf") and abs(same["ssim"] - 1.0) < 1e-6
