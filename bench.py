@@ -51,6 +51,13 @@ WORKLOADS = {
                  "DivideTask vessel.yaml with Nb=64: 64 blocks 64^3, SIREN L=7 f=13, whole-block batch 262144, Adamax"),
     "config1": ((64, 64, 64), 80, 1, 5, 20.0, 0,
                 "SingleTask default.yaml shape: 64^3 u16 block, SIREN L=5 f=22 w0=20, whole-block batch, Adamax"),
+    # sub-volumes with the block shape and width the big configs produce, 8 resp. 4 blocks per GPU
+    "neuron128": ((256, 256, 256), 512, 8, 7, 10.0, 100000,
+                  "DivideTask neuron.yaml geometry (1024^3 ratio 512, auto Nb=512): 128^3 blocks, SIREN L=7 f=19 w0=10, "
+                  "randompoint batch 100000/block, Adamax; 8 blocks per GPU"),
+    "hipct256": ((256, 512, 512), 128, 4, 7, 10.0, 100000,
+                 "DivideTask hipct.yaml geometry (2048^3 ratio 128, Nb=512): 256^3 blocks, SIREN L=7 f=113 w0=10, "
+                 "randompoint batch 100000/block, Adamax; 4 blocks per GPU (fit on the fp32 CUDA-core kernels, decode on tcgen05)"),
 }
 
 
