@@ -1,4 +1,4 @@
-"""Decompress-kernel timing: python tools/eval_sweep.py f L [nets] ; BRIEF_EVAL_CH=<chunks per thread> selects the variant."""
+"""Decompress-kernel timing against the SFU bound: python tools/eval_sweep.py f L [nets]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -21,4 +21,4 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
 vox = nets * dims[0] * dims[1] * dims[2]
 sfu = 4.59e12 / ((L - 1) * f)
-print(f"f={f} L={L} CH={os.environ.get('BRIEF_EVAL_CH', 'default')}: {ms:.3f} ms  {vox / ms / 1e6:.2f} Gvox/s  ({100 * vox / ms / 1e-3 / sfu:.1f}% of the SFU bound {sfu / 1e9:.1f} Gvox/s)  checksum {int(outs[0].view(torch.int16).to(torch.int64).sum())}")
+print(f"f={f} L={L}: {ms:.3f} ms  {vox / ms / 1e6:.2f} Gvox/s  ({100 * vox / ms / 1e-3 / sfu:.1f}% of the SFU bound {sfu / 1e9:.1f} Gvox/s)  checksum {int(outs[0].view(torch.int16).to(torch.int64).sum())}")
