@@ -19,7 +19,8 @@
 
 namespace brief {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;      // default CTA size
+constexpr int kMaxThreads = 512;   // wide networks (small TM): more output-feature groups per sample row
 
 __host__ __device__ inline int row_stride(int F4) { return F4 + (((F4 >> 2) & 1) ? 0 : 4); }
 
@@ -114,7 +115,7 @@ __device__ __forceinline__ float last_layer(const NetDev& n, const float* __rest
 }
 
 // ---- forward / decompress ----------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) simt_eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(kMaxThreads) simt_eval_kernel(EvalArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ NetDev sn;
   int net_id;
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(kThreads) simt_eval_kernel(EvalArgs a) {
   }
   load_net(sn, a.nets[net_id]);
   const NetDev& n = sn;
-  const int TM = a.TM, G = kThreads / TM;
+  const int NT = blockDim.x;
+  const int TM = a.TM, G = NT / TM;
   const int t = threadIdx.x, m = t % TM, g = t / TM;
   const int S = row_stride(n.F4);
   const float* P = a.params + n.param_off;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) simt_eval_kernel(EvalArgs a) {
 }
 
 // ---- fit: gather + forward + weighted L2 + backward -> per-slice gradient partials ---------------
-__global__ void __launch_bounds__(kThreads) simt_fit_kernel(FitArgs a) {
+__global__ void __launch_bounds__(kMaxThreads) simt_fit_kernel(FitArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ NetDev sn;
   const int wi = find_work(a.work_prefix, a.n_work, blockIdx.x);
@@ -192,7 +194,8 @@ __global__ void __launch_bounds__(kThreads) simt_fit_kernel(FitArgs a) {
   load_net(sn, a.nets[net_id]);
   const NetDev& n = sn;
   const int slice = blockIdx.x - a.work_prefix[wi];
-  const int TM = a.TM, G = kThreads / TM;
+  const int NT = blockDim.x;
+  const int TM = a.TM, G = NT / TM;
   const int t = threadIdx.x, m = t % TM, g = t / TM;
   const int F4 = n.F4, S = row_stride(F4), nl = n.L - 1;  // nl sine layers
   const float* P = a.params + n.param_off;
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) simt_fit_kernel(FitArgs a) {
         float* dst = part + dl_Wlast(n) + t;
         *dst = it ? *dst + acc : acc;
       }
-      if (t == kThreads - 1) {
+      if (t == NT - 1) {
         float acc = 0.f;
         for (int i = 0; i < TM; ++i) acc += DY[i];
         float* dst = part + dl_blast(n);
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(kThreads) simt_fit_kernel(FitArgs a) {
       const float* W = P + dl_W(n, l);
       const int nb = F4 >> 2;
       // dW_l[o][k] = sum_m dz[m][o] a[m][k]   (4x4 register tiles, lanes consecutive in k)
-      for (int id = t; id < nb * nb; id += kThreads) {
+      for (int id = t; id < nb * nb; id += NT) {
         const int o4 = id / nb, k4 = id - o4 * nb;
         float acc[4][4];
 #pragma unroll
@@ -393,6 +396,10 @@ __global__ void sample_indices_kernel(uint64_t seed, uint64_t step, uint32_t net
 }
 
 // ---- host launchers ------------------------------------------------------------------------------------
+// A tile of TM <= 32 rows (wide networks: the activations of all layers fill shared memory, one CTA per SM) is served
+// by 512 threads — 16 output-feature groups per row instead of 4 — so that the SM has 16 warps to hide latency with.
+static int simt_threads(int TM) { return TM <= 32 ? kMaxThreads : TM <= 64 ? 256 : kThreads; }
+
 int simt_pick_tm(int F4, int L, bool fit, size_t smem_limit) {
   const int S = row_stride(F4);
   for (int TM = 128; TM >= 8; TM >>= 1) {
@@ -410,13 +417,13 @@ size_t simt_fit_smem(int F4, int L, int TM) {
 cudaError_t launch_simt_eval(const EvalArgs& a, int n_blocks, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(simt_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  simt_eval_kernel<<<n_blocks, kThreads, smem, st>>>(a);
+  simt_eval_kernel<<<n_blocks, simt_threads(a.TM), smem, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_simt_fit(const FitArgs& a, int n_blocks, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(simt_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  simt_fit_kernel<<<n_blocks, kThreads, smem, st>>>(a);
+  simt_fit_kernel<<<n_blocks, simt_threads(a.TM), smem, st>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_gather(const NetDev* nets, int net_id, const float* axes, const long long* idx, long long batch,
