@@ -667,22 +667,34 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     for (int k = 0; k < n_tiles; ++k) {
       const int sl = k & 1;
       if (k >= 2) mbar_wait(&bar_gfree[sl], (uint32_t)((k >> 1) - 1) & 1);
+      // three passes so that the four rows' dependent loads (index -> voxel, index -> axis tables) are all in flight
+      // together instead of one row's chain after the other (rows past the slice end read voxel 0 and are zeroed)
+      long long idx[4];
+      bool ok[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const long long s = s_begin + (long long)k * kTile + lane + 32 * h;
+        ok[h] = s < s_end;
+        long long v = 0;
+        if (ok[h]) {
+          if (n.mode == 0) v = s;
+          else if (a.idx) v = a.idx[n.idx_off + s];
+          else v = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
+        }
+        idx[h] = v;
+      }
+      float raw[4], cx[4][3];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        raw[h] = brief_raw_value(n, idx[h]);
+        brief_coords(n, a.axes, idx[h], cx[h][0], cx[h][1], cx[h][2]);
+      }
 #pragma unroll
       for (int h = 0; h < 4; ++h) {
         const int row = lane + 32 * h;
-        const long long s = s_begin + (long long)k * kTile + row;
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, yv = 0.f, wv = 0.f;
-        if (s < s_end) {
-          long long idx;
-          if (n.mode == 0) idx = s;
-          else if (a.idx) idx = a.idx[n.idx_off + s];
-          else idx = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
-          brief_coords(n, a.axes, idx, x0, x1, x2);
-          const float raw = brief_raw_value(n, idx);
-          yv = brief_normalize(n, raw);
-          wv = brief_weight(n, idx, raw);
-        }
-        s_g[sl][row] = make_float4(x0, x1, x2, yv);
+        const float yv = ok[h] ? brief_normalize(n, raw[h]) : 0.f;
+        const float wv = ok[h] ? brief_weight(n, idx[h], raw[h]) : 0.f;
+        s_g[sl][row] = ok[h] ? make_float4(cx[h][0], cx[h][1], cx[h][2], yv) : make_float4(0.f, 0.f, 0.f, 0.f);
         s_gw[sl][row] = wv;
       }
       __syncwarp();
