@@ -463,39 +463,49 @@ __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
   return tmem_cols_pow2(fit_fixed_cols(F, NH) + fit_acc_blocks(NH) * F);
 }
 
+#ifndef BRIEF_FIT_CPT_B64
+#define BRIEF_FIT_CPT_B64 2
+#endif
+#ifndef BRIEF_FIT_CPT_A64
+#define BRIEF_FIT_CPT_A64 2
+#endif
 template <int F>
 struct FitCfg {
   static constexpr int NC = F / 16;                       // 16-column chunks per row
-  static constexpr int CPT = (F == 64 || F == 32) ? 2 : 1;  // chunks per thread
-  static constexpr int CG = NC / CPT;                     // column groups per role
-  static constexpr int GW = 4 * CG;                       // warps per role (A or B)
-  static constexpr int GT = GW * 32;                      // threads per role
-  static constexpr int THREADS = 2 * GT + 64;             // + MMA-issue warp + sampler warp
+  // chunks per thread of the backward group (A) and of the forward group (B).  Measured at F = 64 (back to back):
+  // A2/B2 (8 + 8 warps) 165 us, A2/B1 (8 + 16 warps) 173 us, A1/B2 (16 + 8) 175 us — more warps on one role lengthen
+  // the other role's epilogues (shared XU / issue slots) by more than they shorten its own
+  static constexpr int CPT_A = F == 64 ? BRIEF_FIT_CPT_A64 : F == 32 ? 2 : 1;
+  static constexpr int CPT_B = F == 64 ? BRIEF_FIT_CPT_B64 : CPT_A;
+  static constexpr int CG_A = NC / CPT_A, CG_B = NC / CPT_B;  // column groups per role
+  static constexpr int GW_A = 4 * CG_A, GW_B = 4 * CG_B;      // warps per role
+  static constexpr int THREADS = (GW_A + GW_B) * 32 + 64;     // + MMA-issue warp + sampler warp
   static constexpr int MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 3;  // must match tc_fit_ctas_per_sm()
 };
 
 template <int F>
 __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_fit_kernel(FitArgs a) {
   using C = FitCfg<F>;
-  constexpr int CPT = C::CPT, CG = C::CG, GW = C::GW, GT = C::GT, NC = C::NC;
-  constexpr int NW = 2 * GW;  // epilogue warps: [0, GW) group B (forward), [GW, 2 GW) group A (backward)
+  constexpr int GW_A = C::GW_A, GW_B = C::GW_B, CG_B = C::CG_B, NC = C::NC;
+  constexpr int NW = GW_A + GW_B;  // epilogue warps: [0, GW_B) group B (forward), [GW_B, NW) group A (backward)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
   __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_lb, bar_f1, bar_f2, bar_gfull[2], bar_gfree[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float4 s_g[2][kTile];  // sampler staging: (x0, x1, x2, normalised target) per row
   __shared__ float s_gw[2][kTile];                //                  loss weight per row
-  __shared__ float s_y[CG][kTile];
+  __shared__ float s_y[CG_B][kTile];
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const bool mma_warp = warp == NW, sampler_warp = warp == NW + 1;
-  const bool group_a = warp >= GW && warp < NW;
-  const int gw = group_a ? warp - GW : warp;  // warp index inside the role
+  const bool group_a = warp >= GW_B && warp < NW;
+  const int gw = group_a ? warp - GW_B : warp;  // warp index inside the role
+  const int CPT = group_a ? C::CPT_A : C::CPT_B, CG = group_a ? C::CG_A : C::CG_B;
   const int q = warp & 3, cg = (gw >> 2) % CG, r = 32 * q + lane;
   const int c_base = cg * CPT;                // first 16-column chunk of this thread
 #ifdef BRIEF_TC_TIMING
-  const int tslot = warp == 0 ? 0 : warp == GW ? 16 : warp == NW ? 32 : warp == NW + 1 ? 48 : -1;
+  const int tslot = warp == 0 ? 0 : warp == GW_B ? 16 : warp == NW ? 32 : warp == NW + 1 ? 48 : -1;
 #endif
   TT(k_start);
   const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
@@ -508,14 +518,14 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     mbar_init(&bar_b, 1);
     mbar_init(&bar_f1, 1);
     mbar_init(&bar_f2, 1);
-    mbar_init(&bar_ra, GW);  // "operands of the backward tile are in place": one arrival per warp of group A
-    mbar_init(&bar_rb, GW);  // same for the forward tile / group B
+    mbar_init(&bar_ra, GW_A);  // "operands of the backward tile are in place": one arrival per warp of group A
+    mbar_init(&bar_rb, GW_B);  // same for the forward tile / group B
     // "loss phase done" has its own barrier: group B raises it and the NEXT tile's first bar_rb signal back to back,
     // and a parity wait cannot tell a phase from the one two completions later
-    mbar_init(&bar_lb, GW);
+    mbar_init(&bar_lb, GW_B);
     for (int k = 0; k < 2; ++k) {
       mbar_init(&bar_gfull[k], 1);    // sampler warp: staging slot k holds a tile's samples
-      mbar_init(&bar_gfree[k], GW);   // group B: staging slot k has been consumed
+      mbar_init(&bar_gfree[k], GW_B);   // group B: staging slot k has been consumed
     }
     fence_mbar_init();
   }
@@ -542,7 +552,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     mbar_expect_tx(&bar_w, bytes);
     bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
   }
-  if (!group_a && warp < GW && cg == 0)  // second column group of the dY block is constant zero
+  if (!group_a && warp < GW_B && cg == 0)  // second column group of the dY block is constant zero
     *reinterpret_cast<uint4*>(sDY + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
 
   const uint32_t tm = tmem_base_s;
@@ -735,9 +745,9 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         float v[2][16];
         tmem_ld16(my_tmem, v[0]);
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
+        for (int c = 0; c < C::CPT_B; ++c) {
           tmem_ld_wait();
-          if (c + 1 < CPT) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
+          if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
 #pragma unroll
           for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
@@ -756,16 +766,16 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
       }
       TT(b6);
       // ---- loss (datal2, main.py:176-182), scaled output gradient and dz_NH
-      if (CG > 1) {
+      if (CG_B > 1) {
         s_y[cg][r] = ypart;
-        named_bar_sync(1, GT);
+        named_bar_sync(1, GW_B * 32);
       }
       // every thread of the row forms y, the error and dy itself (same operands, same order: identical values);
       // column group 0 additionally accumulates the loss and writes the dWlast operand block
       float y = s_bl[0];
-      if (CG > 1) {
+      if (CG_B > 1) {
 #pragma unroll
-        for (int c = 0; c < CG; ++c) y += s_y[c][r];
+        for (int c = 0; c < CG_B; ++c) y += s_y[c][r];
       } else {
         y += ypart;
       }
@@ -789,9 +799,9 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         float v[2][16];
         tmem_ld16(my_tmem, v[0]);  // theta_NH is still in Zf: the next forward MMA is issued after this signal
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
+        for (int c = 0; c < C::CPT_B; ++c) {
           tmem_ld_wait();
-          if (c + 1 < CPT) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
+          if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -829,9 +839,9 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         tmem_ld16(tz, vz[0]);
         tmem_ld16(tx, vx[0]);
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) {
+        for (int c = 0; c < C::CPT_A; ++c) {
           tmem_ld_wait();
-          if (c + 1 < CPT) {
+          if (c + 1 < C::CPT_A) {
             tmem_ld16(tz + 16 * (c + 1), vz[(c + 1) & 1]);
             tmem_ld16(tx + 16 * (c + 1), vx[(c + 1) & 1]);
           }
@@ -857,7 +867,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 
   // ---- slice epilogue: loss partial + gradient partials (TMEM -> global), scale removed in fp32
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
-  if (warp < GW && cg == 0) {
+  if (warp < GW_B && cg == 0) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
     if (lane == 0) s_red[q] = loss_acc;
