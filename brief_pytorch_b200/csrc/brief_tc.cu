@@ -466,6 +466,9 @@ __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
 #ifndef BRIEF_FIT_CPT_B64
 #define BRIEF_FIT_CPT_B64 2
 #endif
+#ifndef BRIEF_FIT_CPT_48
+#define BRIEF_FIT_CPT_48 1
+#endif
 #ifndef BRIEF_FIT_CPT_A64
 #define BRIEF_FIT_CPT_A64 2
 #endif
@@ -475,7 +478,7 @@ struct FitCfg {
   // chunks per thread of the backward group (A) and of the forward group (B).  Measured at F = 64 (back to back):
   // A2/B2 (8 + 8 warps) 165 us, A2/B1 (8 + 16 warps) 173 us, A1/B2 (16 + 8) 175 us — more warps on one role lengthen
   // the other role's epilogues (shared XU / issue slots) by more than they shorten its own
-  static constexpr int CPT_A = F == 64 ? BRIEF_FIT_CPT_A64 : F == 32 ? 2 : 1;
+  static constexpr int CPT_A = F == 64 ? BRIEF_FIT_CPT_A64 : F == 48 ? BRIEF_FIT_CPT_48 : F == 32 ? 2 : 1;
   static constexpr int CPT_B = F == 64 ? BRIEF_FIT_CPT_B64 : CPT_A;
   static constexpr int CG_A = NC / CPT_A, CG_B = NC / CPT_B;  // column groups per role
   static constexpr int GW_A = 4 * CG_A, GW_B = 4 * CG_B;      // warps per role

@@ -375,3 +375,27 @@ def test_config1_3000_steps_quality_tracks_the_reference(prec):
     print(f"[{prec}] psnr {psnr:.4f} (reference {float(g['psnr']):.4f})  ssim {ssim:.5f} (reference {float(g['ssim']):.5f})")
     assert abs(psnr - float(g["psnr"])) < 0.25
     assert abs(ssim - float(g["ssim"])) < 0.004
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
+def test_config1_full_budget_quality_within_north_star_bars(prec):
+    """SingleTask default.yaml's full step budget (20000 full-batch Adamax steps on the shipped block), golden from the
+    unmodified reference on the CPU (oracle/gen_golden_long.py 20000): decoded PSNR within 0.1 dB and SSIM within 0.002
+    of the reference at equal steps (BASELINE.json north_star)."""
+    import os
+    from conftest import GOLD
+    if not os.path.exists(os.path.join(GOLD, "config1_20000.npz")):
+        pytest.skip("tests/golden/config1_20000.npz not generated (oracle/gen_golden_long.py 20000, ~3 h of CPU)")
+    g, g0, vol = load_gold("config1_20000"), load_gold("config1_200"), load_gold("brain64")["volume"]
+    grp = make_group([spec_of(NETS["c1"], (64, 64, 64))], prec)
+    grp.set_axes(0, "-1,1")
+    grp.set_params(0, g0["p0"])
+    bind_block(grp, 0, vol, rules=[(65535, 65535, 1.0)], tau=float(g0["thr"]))
+    grp.set_sampler(0, "randomcube")
+    grp.fit_run(int(g["steps"]), "Adamax", 1e-3, milestones=(50000, 60000, 70000), gamma=0.2)
+    dec = u16(grp.decompress("uint16")[0])[..., None]
+    a = vol.astype(np.float32)
+    psnr, ssim = O.cal_psnr(a, dec.astype(np.float32), 65535), O.cal_ssim(a, dec.astype(np.float32), 65535)
+    print(f"[{prec}] psnr {psnr:.4f} (reference {float(g['psnr']):.4f})  ssim {ssim:.5f} (reference {float(g['ssim']):.5f})")
+    assert abs(psnr - float(g["psnr"])) < 0.1
+    assert abs(ssim - float(g["ssim"])) < 0.002
