@@ -226,11 +226,11 @@ class NFGR:
             grp.set_axes(i, str(self.opt["Compress"]["coords_mode"]))
             grp.set_params(i, pack_module_params(m))
             grp.set_denorm(i, float(s["min"]), float(s["max"]), lo, hi)
-        outs = grp.decompress(dtype)
+        outs = grp.decompress_to_host(dtype)  # block i's device->host copy runs under the decode of block i+1
         clip = self.opt["Decompress"]["postprocess"]["clip"]
         res = []
         for t, s in zip(outs, sideinfos):
-            a = t.cpu().numpy()
+            a = t.numpy()
             a = a.view(np.uint16) if dtype == "uint16" else a
             a = a.reshape(tuple(s["data_shape"]))
             level = self.opt["Decompress"]["postprocess"]["denoise"]["level"]

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kMaxThreads) simt_eval_kernel(EvalArgs a) {
     const int wi = find_work(a.work_prefix, a.n_work, blockIdx.x);
     net_id = a.work_net[wi];
     tile = blockIdx.x - a.work_prefix[wi];
+    if (a.out_ptrs[net_id] == nullptr) return;  // this network is not part of the call
   }
   load_net(sn, a.nets[net_id]);
   const NetDev& n = sn;

@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
     const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
     net_id = a.work_net[wi];
     chunk = blockIdx.x - a.work_prefix[wi];
+    if (a.out_ptrs[net_id] == nullptr) return;  // this network is not part of the call (CTA-uniform, before any barrier)
   }
   tc_load_net(sn, a.nets[net_id]);
   if (t == 0) {

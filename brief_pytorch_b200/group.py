@@ -249,16 +249,44 @@ class SirenGroup:
         out = out.reshape(*coords.shape[:-1], 1)
         return (out, layers) if return_layers else out
 
-    def decompress(self, out_dtype: str = "uint16", out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+    def decompress(self, out_dtype: str = "uint16", out: Optional[List[Optional[torch.Tensor]]] = None,
+                   nets: Optional[Sequence[int]] = None) -> List[Optional[torch.Tensor]]:
         """Dense-grid evaluation + inverse normalisation + truncating cast for every network (one launch
-        per kernel family).  Returns one tensor per network shaped like its block (uint16 as int16 bits)."""
+        per kernel family).  Returns one tensor per network shaped like its block (uint16 as int16 bits).
+        `nets`: decode only these networks (the others' entries stay None / untouched) — lets a caller overlap the
+        device->host copy of one block with the decode of the next."""
         dt = _NP2DT[out_dtype]
+        want = set(range(len(self.specs))) if nets is None else set(int(i) for i in nets)
         if out is None:
-            out = [torch.empty(tuple(int(x) for x in s.dims), dtype=_DT2TORCH[dt], device=self.device) for s in self.specs]
-        ptrs = (C.c_void_p * len(out))(*[t.data_ptr() for t in out])
+            out = [torch.empty(tuple(int(x) for x in s.dims), dtype=_DT2TORCH[dt], device=self.device) if i in want else None
+                   for i, s in enumerate(self.specs)]
+        ptrs = (C.c_void_p * len(out))(*[(t.data_ptr() if (t is not None and i in want) else None) for i, t in enumerate(out)])
         with torch.cuda.device(self.device):
             check(self._lib.brief_decompress(self._h, ptrs, dt, _stream(self.device)))
         return out
+
+    def decompress_to_host(self, out_dtype: str = "uint16", host_out: Optional[List[torch.Tensor]] = None,
+                           dev_out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """Decode block by block and overlap every block's device->host copy (copy stream, pinned destination) with the
+        decode of the next one.  Returns the pinned host tensors (uint16 as int16 bit patterns)."""
+        dt = _DT2TORCH[_NP2DT[out_dtype]]
+        n = len(self.specs)
+        shapes = [tuple(int(x) for x in s.dims) for s in self.specs]
+        if host_out is None:
+            host_out = [torch.empty(sh, dtype=dt).pin_memory() for sh in shapes]
+        if dev_out is None:
+            dev_out = [torch.empty(sh, dtype=dt, device=self.device) for sh in shapes]
+        main = torch.cuda.current_stream(self.device)
+        copy = torch.cuda.Stream(device=self.device)
+        for i in range(n):
+            self.decompress(out_dtype, out=dev_out, nets=[i])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(ev)
+                host_out[i].copy_(dev_out[i], non_blocking=True)
+        copy.synchronize()
+        return host_out
 
     def gather(self, net: int, idx: Optional[torch.Tensor], batch: Optional[int] = None):
         """The reference sampler's (coords, data, weight) for the given voxel indices (main.py:156-160)."""

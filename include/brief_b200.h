@@ -184,7 +184,8 @@ int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n
 /* Replaces reconstruct_flattened + invnormalize_data (utils/misc.py:59-92, utils/io.py:136-147) for every
  * network of the group in one launch: dense grid generated on chip from the axis tables, evaluated, then
  * ((y - lo) / (hi - lo)) clipped to [0,1], * (vmax - vmin) + vmin, truncating cast to out_dtype.
- * host_dev_out[i] is the device destination of network i (dims[0]*dims[1]*dims[2] elements, contiguous);
+ * host_dev_out[i] is the device destination of network i (dims[0]*dims[1]*dims[2] elements, contiguous), or NULL to
+ * leave network i out of this call (a caller that overlaps decode with device->host copies decodes block by block);
  * out_dtype BRIEF_F32 skips the inverse normalisation and stores the raw network output.
  * vmin/vmax/lo/hi default to the values given to brief_group_bind_volume, or override with
  * brief_group_set_denorm for decode-only groups. */
