@@ -9,7 +9,8 @@
 //   reconstruct_flattened        utils/misc.py:59-92 (dense grid generated on chip)
 //   invnormalize_data            utils/io.py:136-147 (epilogue)
 //
-// One CTA = 128 threads = one tile of TM samples of one network; thread t serves sample
+// One CTA = 128 .. 512 threads (512 when the tile is <= 32 rows, i.e. wide networks) = one tile of TM samples of one
+// network; thread t serves sample
 // m = t % TM and output-feature group g = t / TM.  Activations live in shared memory, sample-major
 // [TM][S] with S/4 odd so that per-sample float4 row reads are bank-conflict free.  Weights are
 // read with warp-uniform 16-byte __ldg (L1 resident).  Each layer is a register-blocked

@@ -5,12 +5,16 @@
 //                                                               utils/io.py:136-147            -> tc_eval_kernel
 //   sampler gather + forward + datal2 + backward               main.py:126-163, 176-182, 385-396 -> tc_fit_kernel
 //
-// Shape of the computation.  One CTA = 128 threads = one tile of 128 samples (UMMA M = 128): thread t owns sample
-// row t == TMEM lane t.  The first layer (K = 3) and the last layer (N = 1) run on CUDA cores in fp32; every
-// hidden layer z_l = a_{l-1} W_l^T is a tcgen05.mma (fp16 operands from shared memory, fp32 accumulator in TMEM),
-// followed by an epilogue that reads the accumulator row with tcgen05.ld, applies sin(w*z + w*b) and writes the
-// fp16 activations straight back into the shared-memory operand buffer of the next layer.  The network's weights
-// are staged ONCE per CTA by one bulk (TMA) copy of the packed fp16 image and stay resident for all its tiles.
+// Shape of the computation.  A tile is 128 samples (UMMA M = 128): one thread per sample row == TMEM lane, a warp may
+// only touch the lane quadrant 32 * (warp % 4).  EVERY sine layer's argument comes out of a tcgen05.mma (fp16 operands,
+// fp32 accumulator in TMEM): the packed operand image (brief_image.cuh) carries omega and the bias inside the weights
+// (two constant-one activation columns f, f+1 hold the bias as an fp16 hi/lo pair), layer 0 is one K = 16 MMA against the
+// hi/lo-split coordinate row, and in the decompress kernel the last layer is an N = 16 MMA against hi/lo-split Wlast.
+// An epilogue therefore is: tcgen05.ld the accumulator row, FMUL.RZ + MUFU.SIN per element, pack to fp16, write the row
+// into the next contraction's operand (shared memory; in the fit kernel also tensor memory).  A network's image is staged
+// ONCE per CTA by one bulk (TMA) copy and stays resident for all of the CTA's tiles.  MMAs are issued by a dedicated warp
+// (a tcgen05.mma blocks its issuing thread for about as long as it executes), told through mbarriers when a tile's
+// operand rows are written; the epilogue warps only ever wait for the commit of the MMAs they consume.
 //
 // Why fp16 and not bf16: activations are sines (|a| <= 1) and weights are << 1, so fp16's 11-bit significand is
 // usable without range problems and gives 8x smaller rounding error than bf16 at the same tensor rate.  A and B of
@@ -20,17 +24,13 @@
 // the scale is removed in fp32 when the accumulated dW leaves TMEM.
 //
 // Operand layout: brief_umma.cuh ("interleaved" 8x8 cores).  Width f is padded to F = F_PAD (multiple of 16,
-// F > f); pad weights are zero.  Column f of every activation buffer is the constant 1 (its packed "bias" makes
-// the sine argument pi/2), so bias gradients fall out of the dW contractions as column f.
+// F >= f + 2); pad weights are zero.  Because columns f, f+1 of every activation buffer are the constant 1, the bias
+// gradients fall out of the dW contractions as column f.
 //
-// Fit kernel, per tile:   forward  NH x [ MMA z_l ; sin ]            (activations a_0..a_NH stay in shared memory)
-//                         backward NH x [ MMA dW_l += dz_l^T a_{l-1} ; MMA z_{l-1} (recomputed) ; MMA dX = dz_l W_l ;
-//                                         dz_{l-1} = dX * w * cos(w z_{l-1}) ]
-// dW_l accumulate ACROSS the tiles of a slice in TMEM (M = 64 accumulators, F columns per layer) and are written
-// once per slice to the slice's gradient-partial slot; the optimiser kernel reduces slots in fixed order.
-//
-// Roofline: per sample a hidden layer costs 2*F*F tensor FLOPs and F special-function ops (2F in the fit).  At
-// F <= 64 the MUFU pipe (16 ops/clk/SM), not the tensor pipe, is the binding unit.
+// Decompress kernel: up to 4 groups x 2 alternating tile slots per CTA share one image (8 tiles in flight per SM);
+// bound by the special-function unit (XU pipe 76 %).  Fit kernel: two tiles in flight on separate warp groups (forward /
+// backward), event-driven MMA-issue warp, dW accumulated across the slice's tiles in TMEM; bound by a latency chain on
+// a tensor pipe whose N = 64 SS-mode contractions are operand-fetch-limited.
 #include <cuda_fp16.h>
 #include <cstdlib>
 
@@ -145,20 +145,8 @@ __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_buf, uint32_t b_
 }
 
 // ==================================================================================================================
-// thread mapping shared by both kernels
+// operand-row stores shared by both kernels (thread = row r, chunk = 16 columns = two 16-byte core-matrix rows)
 // ==================================================================================================================
-// A CTA has 128 * (F/16) threads.  Warp w serves TMEM lane quadrant q = w & 3 (rows 32q .. 32q+31 of the tile, the
-// only lanes tcgen05.ld lets it touch) and column group cg = w >> 2 (columns 16cg .. 16cg+15): every thread owns
-// ONE 16-column chunk of its sample row per layer, so a hidden-layer epilogue is one tcgen05.ld.x16 + 16 sines +
-// two 16-byte operand stores, and an SM holds 4 warps per scheduler for F = 64 instead of 1.
-template <int F>
-struct TcCfg {
-  static constexpr int CW = F / 16;
-  static constexpr int THREADS = 128 * CW;                                // epilogue threads
-  static constexpr int FIT_THREADS = THREADS + 64;                        // + MMA-issue warp + sampler warp
-  static constexpr int FIT_MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 4;    // must match tc_fit_ctas_per_sm()
-};
-
 // 16 fp32 -> 8 packed f16x2 words -> the operand row in shared memory and (optionally) the A-operand row in TMEM
 template <bool SAT>
 __device__ __forceinline__ void store_chunk16_both(unsigned char* buf, int r, int cg, const float* v, bool to_tmem,
@@ -175,14 +163,6 @@ __device__ __forceinline__ void store_chunk16(unsigned char* buf, int r, int cg,
       make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
   *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg + 1, kTile)) =
       make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
-}
-__device__ __forceinline__ void store_chunk16_sat(unsigned char* buf, int r, int cg, const float* v) {
-  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg, kTile)) =
-      make_uint4(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3]), pack_f16x2_sat(v[4], v[5]),
-                 pack_f16x2_sat(v[6], v[7]));
-  *reinterpret_cast<uint4*>(buf + chunk_off(r, 2 * cg + 1, kTile)) =
-      make_uint4(pack_f16x2_sat(v[8], v[9]), pack_f16x2_sat(v[10], v[11]), pack_f16x2_sat(v[12], v[13]),
-                 pack_f16x2_sat(v[14], v[15]));
 }
 
 // ==================================================================================================================
