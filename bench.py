@@ -424,6 +424,35 @@ def main():
     stats_gbs = big.numel() * 2 / t_stats / 1e9
     del big
 
+    # ---- the sampler's random gather (main.py:154-163) standalone: voxel indices -> (coords, normalised value, weight)
+    #      from a volume far larger than L2, so that every sample costs one DRAM sector ----
+    gshape = (256, 1024, 1024)  # 512 MiB of uint16 voxels, 4x the L2
+    gvol = torch.empty(gshape, dtype=torch.int16, device=dev)
+    gvol.random_(0, 30000)
+    ggrp = SirenGroup([NetSpec(plan["features"], plan["layers"], plan["w0"], gshape)], dev, args.precision)
+    ggrp.bind_volume(0, gvol, 0.0, 30000.0, 0.0, 100.0, rules=[(10001, 65535, 0.1)], np_dtype="uint16")
+    n_g = 1 << 24
+    gidx = torch.randint(0, gvol.numel(), (n_g,), dtype=torch.int64, device=dev)
+    ggrp.gather(0, gidx)
+    torch.cuda.synchronize()
+    g0e, g1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_g = 0.0
+    for _ in range(5):
+        g0e.record()
+        ggrp.gather(0, gidx)
+        g1e.record()
+        torch.cuda.synchronize()
+        t_g += g0e.elapsed_time(g1e) / 1e3
+    t_g /= 5
+    gather_stats = {"samples_per_s": n_g / t_g,
+                    "useful_gbs": n_g * (8 + 2 + 20) / t_g / 1e9,          # index + voxel read, 3 coords + value + weight written
+                    "sector_gbs": n_g * (8 + 32 + 20) / t_g / 1e9,         # a random 2-byte read moves a 32-byte sector
+                    "note": "brief_gather on 16 Mi random voxels of a 512 MiB uint16 volume (4x L2): coords + normalised value "
+                            "+ weight materialised like the reference sampler; the fit kernels fuse this gather instead"}
+    gather_stats["hbm_frac_sector"] = gather_stats["sector_gbs"] / pk["hbm_gbs"]
+    ggrp.close()
+    del gvol, gidx
+
     # ---- NCCL, after the hot path: decoded blocks -> rank 0 (variable-size send/recv), checked by a checksum table ----
     gather = None
     if world > 1:
@@ -492,6 +521,7 @@ def main():
         line["block_stats"] = {"gbs": stats_gbs, "hbm_frac": stats_gbs / pk["hbm_gbs"], "bytes": 2 << 30,
                                "note": "min/max/sum/sum^2 of a 2 GiB uint16 buffer, one launch incl. its 2 tiny copies; "
                                        "rank 0's figure; peak = " + pk["src"] + " copy bandwidth (read+write)"}
+        line["sampler_gather"] = gather_stats
         if gather is not None:
             line["gather_decoded_blocks"] = gather
         if world == 1 and not args.no_cpu_baseline:

@@ -127,10 +127,19 @@ __device__ __forceinline__ float brief_weight(const NetDev& n, long long idx, fl
 __device__ __forceinline__ void brief_coords(const NetDev& n, const float* __restrict__ axes, long long idx,
                                              float& c0, float& c1, float& c2) {
   const float* ax = axes + n.axis_off;
-  int x = (int)(idx % n.w);
-  long long r = idx / n.w;
-  int y = (int)(r % n.h);
-  int z = (int)(r / n.h);
+  int x, y, z;
+  if (n.n_vox <= 0x7fffffffLL) {  // 32-bit index arithmetic (a 64-bit div/mod pair costs ~10x as many instructions)
+    const unsigned i = (unsigned)idx, w = (unsigned)n.w, h = (unsigned)n.h;
+    const unsigned r = i / w;
+    x = (int)(i - r * w);
+    z = (int)(r / h);
+    y = (int)(r - (unsigned)z * h);
+  } else {
+    x = (int)(idx % n.w);
+    const long long r = idx / n.w;
+    y = (int)(r % n.h);
+    z = (int)(r / n.h);
+  }
   if (n.in_dim == 3) {
     c0 = __ldg(ax + z);
     c1 = __ldg(ax + n.d + y);

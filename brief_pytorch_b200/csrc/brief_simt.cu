@@ -370,23 +370,42 @@ __global__ void __launch_bounds__(kMaxThreads) simt_fit_kernel(FitArgs a) {
 }
 
 // ---- reference sampler outputs materialised (main.py:156-160) ---------------------------------------
-__global__ void gather_kernel(const NetDev* nets, int net_id, const float* __restrict__ axes,
-                              const long long* __restrict__ idx, long long batch, float* coords, float* data,
-                              float* weight) {
-  const NetDev& n = nets[net_id];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < batch;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long v = idx ? idx[i] : i;
-    float c0, c1, c2;
-    brief_coords(n, axes, v, c0, c1, c2);
-    const float raw = brief_raw_value(n, v);
-    if (coords) {
-      coords[i * n.in_dim] = c0;
-      coords[i * n.in_dim + 1] = c1;
-      if (n.in_dim == 3) coords[i * n.in_dim + 2] = c2;
+// HBM-bound on random sectors: the descriptor is staged in shared memory once, and every thread keeps FOUR samples'
+// dependent chains (index -> voxel, index -> axis tables) in flight before it normalises and stores.
+__global__ void __launch_bounds__(256) gather_kernel(const NetDev* nets, int net_id, const float* __restrict__ axes,
+                                                     const long long* __restrict__ idx, long long batch, float* coords,
+                                                     float* data, float* weight) {
+  __shared__ NetDev sn;
+  load_net(sn, nets[net_id]);
+  const NetDev& n = sn;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < batch; i0 += 4 * stride) {
+    long long v[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long i = i0 + k * stride;
+      ok[k] = i < batch;
+      v[k] = ok[k] ? (idx ? __ldg(idx + i) : i) : 0;
     }
-    if (data) data[i] = brief_normalize(n, raw);
-    if (weight) weight[i] = brief_weight(n, v, raw);
+    float raw[4], c[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      raw[k] = brief_raw_value(n, v[k]);
+      brief_coords(n, axes, v[k], c[k][0], c[k][1], c[k][2]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const long long i = i0 + k * stride;
+      if (coords) {
+        coords[i * n.in_dim] = c[k][0];
+        coords[i * n.in_dim + 1] = c[k][1];
+        if (n.in_dim == 3) coords[i * n.in_dim + 2] = c[k][2];
+      }
+      if (data) data[i] = brief_normalize(n, raw[k]);
+      if (weight) weight[i] = brief_weight(n, v[k], raw[k]);
+    }
   }
 }
 
