@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   constexpr int NW = GW_A + GW_B;  // epilogue warps: [0, GW_B) group B (forward), [GW_B, NW) group A (backward)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_lb, bar_f1, bar_f2, bar_gfull[2], bar_gfree[2];
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_lb, bar_f1, bar_f2[2], bar_gfull[2], bar_gfree[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float4 s_g[2][kTile];  // sampler staging: (x0, x1, x2, normalised target) per row
   __shared__ float s_gw[2][kTile];                //                  loss weight per row
@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     mbar_init(&bar_a, 1);
     mbar_init(&bar_b, 1);
     mbar_init(&bar_f1, 1);
-    mbar_init(&bar_f2, 1);
+    mbar_init(&bar_f2[0], 1);  // "tile complete", one barrier per tile parity: the waiter (group B, two tiles later) can
+    mbar_init(&bar_f2[1], 1);  // never see two completions of the same barrier before it has consumed the first
     mbar_init(&bar_ra, GW_A);  // "operands of the backward tile are in place": one arrival per warp of group A
     mbar_init(&bar_rb, GW_B);  // same for the forward tile / group B
     // "loss phase done" has its own barrier: group B raises it and the NEXT tile's first bar_rb signal back to back,
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
             if (zb2 && l >= 2) recompute(l - 2);  // next stage's theta, behind this stage's dW
           } else {  // dW0 += dz_0^T [x_hi, 1, x_lo, ...]; completes the tile
             issue_dw<16>(acc_addr(NH), aDz + (uint32_t)(sbA ^ (NH & 1)) * BUF, aX + pa * BLK, accum);
-            commit(&bar_f2);
+            commit(&bar_f2[pa]);
           }
         }
         __syncwarp();
@@ -702,7 +703,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     for (int k = 0; k < n_tiles; ++k) {
       const int p = k & 1;
       TT(b0);
-      if (k >= 2) mbar_wait(&bar_f2, (uint32_t)k & 1);  // tile k-2 complete: ring slots of this parity and sX[p] are free
+      if (k >= 2) mbar_wait(&bar_f2[p], (uint32_t)((k >> 1) - 1) & 1);  // tile k-2 complete: ring slots of this parity and sX[p] are free
       TT(b1);
       mbar_wait(&bar_gfull[p], (uint32_t)(k >> 1) & 1);
       TT(b2);
