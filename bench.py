@@ -422,7 +422,38 @@ def main():
         t_stats += s0.elapsed_time(s1) / 1e3
     t_stats /= 5
     stats_gbs = big.numel() * 2 / t_stats / 1e9
-    del big
+
+    # ---- preprocess (utils/misc.py:244-254) on the device: threshold + 2x2x2 opening + zeroing, in place, on the same
+    #      2 GiB buffer seen as one 1024^3 block whose lower half is dark (below the level) ----
+    from brief_pytorch_b200.group import preprocess_
+    vol3 = big.view(1024, 1024, 1024)
+    vol3[:512] >>= 6                      # values < 469: a solid region the opening keeps
+    pre_scratch = torch.empty(2 * 1024 * 1024 * 32 * 4, dtype=torch.uint8, device=dev)
+    preprocess_(vol3, 500, [2, 2, 2], [0, 65535], "uint16", scratch=pre_scratch)
+    zeroed = int((vol3[:512] == 0).sum()) + int((vol3[512:] == 0).sum())
+    t_pre = 0.0
+    for _ in range(5):
+        s0.record()
+        preprocess_(vol3, 500, [2, 2, 2], [0, 65535], "uint16", scratch=pre_scratch)
+        s1.record()
+        torch.cuda.synchronize()
+        t_pre += s0.elapsed_time(s1) / 1e3
+    t_pre /= 5
+    pre_stats = {"voxels_per_s": big.numel() / t_pre, "ms": 1e3 * t_pre,
+                 "gbs": (big.numel() * 2 + zeroed * 2) / t_pre / 1e9, "zeroed_voxels": zeroed,
+                 "note": "brief_preprocess on a 1024^3 uint16 block (2 GiB, 16x L2), level 500, close [2,2,2], clip = dtype "
+                         "range: 3 launches (mask, opening, apply); algorithmic bytes = the block read once + 2 B per "
+                         "zeroed voxel written"}
+    pre_stats["hbm_frac"] = pre_stats["gbs"] / pk["hbm_gbs"]
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import brief_oracle as O_pre  # cpu_baseline leg: the reference's host path timed beside the kernel
+        samp = vol3[448:512, :256, :256].cpu().numpy().view(np.uint16)[..., None].copy()  # 64 x 256 x 256
+        t0 = time.perf_counter()
+        O_pre.preprocess(samp, 500, [2, 2, 2], [0, 65535])
+        pre_stats["cpu_voxels_per_s"] = samp.size / (time.perf_counter() - t0)
+        pre_stats["cpu_sample"] = "the reference's scipy.ndimage call on one 64x256x256 block (1 thread)"
+    del big, vol3, pre_scratch
 
     # ---- the sampler's random gather (main.py:154-163) standalone: voxel indices -> (coords, normalised value, weight)
     #      from a volume far larger than L2, so that every sample costs one DRAM sector ----
@@ -522,6 +553,7 @@ def main():
                                "note": "min/max/sum/sum^2 of a 2 GiB uint16 buffer, one launch incl. its 2 tiny copies; "
                                        "rank 0's figure; peak = " + pk["src"] + " copy bandwidth (read+write)"}
         line["sampler_gather"] = gather_stats
+        line["preprocess"] = pre_stats
         if gather is not None:
             line["gather_decoded_blocks"] = gather
         if world == 1 and not args.no_cpu_baseline:

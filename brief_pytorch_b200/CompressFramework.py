@@ -22,7 +22,7 @@ import torch
 import yaml
 
 from . import misc, sharding
-from .group import NetSpec, SirenGroup, block_stats, pack_module_params, unpack_module_params
+from .group import NetSpec, SirenGroup, block_stats, pack_module_params, preprocess_, unpack_module_params
 from .io import get_type_max
 from .ModelSave import load_model, save_model
 from .Networks import ALL_CALC_PHI_FEATURES, ALL_CALC_PHI_PARAM_COUNT, get_nnmodule_param_count, init_phi
@@ -157,6 +157,17 @@ class NFGR:
         if len({r.dtype for r in raws}) != 1:
             raise NotImplementedError("blocks of one volume share a dtype")
         dev_raw = [torch.from_numpy(r.view(np.int16) if r.dtype == np.uint16 else r).to(grp.device) for r in raws]
+        pre = C.get("preprocess")
+        if pre and raws and not misc.preprocess_is_identity(raws[0].dtype, pre["denoise"]["level"], pre["clip"]):
+            # main.py:336-337, per block like the reference's per-block processes: threshold + opening + clip on the
+            # device copy (brief_preprocess); min / max and the weights below are those of the preprocessed block
+            misc._limits(raws[0], pre["clip"][0], pre["clip"][1])
+            needs_host = any(r.split("_")[0] in ("quantile", "exp") for r in C["loss"]["weight"])
+            for i, t in enumerate(dev_raw):
+                preprocess_(t, pre["denoise"]["level"], pre["denoise"]["close"], pre["clip"], raws[i].dtype.name)
+                if needs_host:
+                    h = t.cpu().numpy()
+                    raws[i] = h.view(np.uint16) if raws[i].dtype == np.uint16 else h
         stats = block_stats(dev_raw, raws[0].dtype.name)
         for i, b in enumerate(blocks):
             grp.set_axes(i, str(C["coords_mode"]))
@@ -226,22 +237,21 @@ class NFGR:
             grp.set_axes(i, str(self.opt["Compress"]["coords_mode"]))
             grp.set_params(i, pack_module_params(m))
             grp.set_denorm(i, float(s["min"]), float(s["max"]), lo, hi)
-        outs = grp.decompress_to_host(dtype)  # block i's device->host copy runs under the decode of block i+1
-        clip = self.opt["Decompress"]["postprocess"]["clip"]
+        post_opt = self.opt["Decompress"]["postprocess"]
+        level, close, clip = post_opt["denoise"]["level"], post_opt["denoise"]["close"], post_opt["clip"]
+        post = None
+        if dtype in ("uint8", "uint16") and not misc.preprocess_is_identity(dtype, level, clip):
+            misc._limits(np.zeros(0, dtype), clip[0], clip[1])
+            post = lambda i, t: preprocess_(t, level, close, clip, dtype)  # main.py:295, on the device before the copy
+        elif dtype not in ("uint8", "uint16") and level > 0:
+            raise NotImplementedError(f"denoise postprocess of {dtype} blocks")
+        outs = grp.decompress_to_host(dtype, post=post)  # block i's device->host copy runs under the decode of block i+1
         res = []
         for t, s in zip(outs, sideinfos):
             a = t.numpy()
             a = a.view(np.uint16) if dtype == "uint16" else a
             a = a.reshape(tuple(s["data_shape"]))
-            level = self.opt["Decompress"]["postprocess"]["denoise"]["level"]
-            if level > 0:  # utils/misc.py:244-254 (a no-op at the shipped level 0 for unsigned data)
-                from scipy import ndimage
-                close = self.opt["Decompress"]["postprocess"]["denoise"]["close"]
-                if close is False:
-                    a[a <= level] = 0
-                else:
-                    a[ndimage.binary_opening(a <= level, structure=np.ones(tuple(close) + (1,)), iterations=1)] = 0
-            res.append(a.clip(clip[0], clip[1]))
+            res.append(a if dtype in ("uint8", "uint16") else a.clip(clip[0], clip[1]))
         grp.close()
         return res
 

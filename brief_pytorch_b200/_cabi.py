@@ -73,6 +73,9 @@ PROTOTYPES = {
     "brief_block_stats": (c_i32, [C.POINTER(c_vp), C.POINTER(c_i64), c_i32, c_i32, c_i32, C.POINTER(C.c_double), c_vp]),
     "brief_deblock": (c_i32, [c_vp, c_i32, c_i32, c_i32, C.POINTER(c_i32), c_i32, c_i32, c_i32, c_i32, C.POINTER(c_i32), c_i32, c_vp]),
     "brief_volume_quality": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, C.c_double, C.POINTER(C.c_double), c_i32, c_vp]),
+    "brief_preprocess_scratch_bytes": (c_i64, [c_i32, c_i32, c_i32]),
+    "brief_preprocess": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, C.c_double, C.POINTER(c_i32), C.c_double, C.c_double, c_vp,
+                                 c_i32, c_vp]),
     "brief_launch_count": (c_i64, []),
     "brief_reset_launch_count": (None, []),
 }

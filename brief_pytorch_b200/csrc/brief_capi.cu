@@ -910,6 +910,50 @@ int brief_volume_quality(const void* dev_a, const void* dev_b, int32_t dtype, in
   return 0;
 }
 
+int64_t brief_preprocess_scratch_bytes(int32_t depth, int32_t height, int32_t width) {
+  if (depth < 1 || height < 1 || width < 1) return 0;
+  return (int64_t)preprocess_scratch_bytes(depth, height, width);
+}
+
+int brief_preprocess(void* dev_volume, int32_t dtype, int32_t depth, int32_t height, int32_t width, double level,
+                     const int32_t* host_close, double clip_lo, double clip_hi, void* dev_scratch, int32_t device,
+                     void* stream) {
+  if (!dev_volume || !dev_scratch || depth < 1 || height < 1 || width < 1)
+    return fail(BRIEF_ERR_INVALID, "brief_preprocess: bad arguments");
+  if (dtype != BRIEF_U8 && dtype != BRIEF_U16)
+    return fail(BRIEF_ERR_UNSUPPORTED, "brief_preprocess: dtype %d (uint8 / uint16 volumes only)", dtype);
+  const double tmax = dtype == BRIEF_U8 ? 255.0 : 65535.0;
+  if (!(clip_lo >= 0 && clip_lo <= clip_hi && clip_hi <= tmax))  // range_limit, utils/tool.py:26-30
+    return fail(BRIEF_ERR_INVALID, "Improper range setting! clip [%g, %g] outside [0, %g]", clip_lo, clip_hi, tmax);
+  int sz = 1, sy = 1, sx = 1;
+  if (host_close) {
+    sz = host_close[0]; sy = host_close[1]; sx = host_close[2];
+    if (sz < 1 || sy < 1 || sx < 1 || sz > 4 || sy > 4 || sx > 4)
+      return fail(BRIEF_ERR_UNSUPPORTED, "brief_preprocess: structure %dx%dx%d (each side 1..4)", sz, sy, sx);
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(BRIEF_ERR_CUDA, "CUDA device %d not available", device);
+  CU(cudaSetDevice(device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  // v <= level on integers: v <= floor(level); nothing qualifies below 0
+  const bool any_mask = level >= 0;
+  const unsigned int thr = (unsigned int)std::min(std::floor(std::max(level, 0.0)), tmax);
+  // numpy clips integer data against the bounds as given: v < lo -> lo means v < ceil(lo); the stored value is the
+  // bound cast to the dtype.  Configs give integers; fractional bounds are rejected rather than guessed at.
+  if (clip_lo != std::floor(clip_lo) || clip_hi != std::floor(clip_hi))
+    return fail(BRIEF_ERR_UNSUPPORTED, "brief_preprocess: fractional clip bounds");
+  const unsigned int lo = (unsigned int)clip_lo, hi = (unsigned int)clip_hi;
+  const bool clip = lo > 0 || hi < (unsigned int)tmax;
+  int launches = 0;
+  cudaError_t e = launch_preprocess(dev_volume, dtype, depth, height, width, thr, any_mask, sz, sy, sx, lo, hi, clip,
+                                    dev_scratch, sms, &launches, (cudaStream_t)stream);
+  g_launches.fetch_add(launches);
+  if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "brief_preprocess: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int brief_block_stats(void* const* host_dev_raw, const int64_t* host_sizes, int32_t n_blocks, int32_t dtype,
                       int32_t device, double* host_out, void* stream) {
   if (!host_dev_raw || !host_sizes || !host_out || n_blocks < 0) return fail(BRIEF_ERR_INVALID, "brief_block_stats: bad arguments");

@@ -97,6 +97,12 @@ cudaError_t launch_deblock(unsigned short* img, int D, int H, int W, const Deblo
 cudaError_t launch_quality(const void* a, const void* b, int dtype, int D, int H, int W, const float* win11, float c1, float c2,
                            double* dev_out, cudaStream_t st);
 
+// brief_preprocess.cu
+size_t preprocess_scratch_bytes(int D, int H, int W);
+cudaError_t launch_preprocess(void* vol, int dtype, int D, int H, int W, unsigned int thr, bool any_mask, int sz, int sy,
+                              int sx, unsigned int lo, unsigned int hi, bool clip, void* scratch, int num_sms, int* launches,
+                              cudaStream_t st);
+
 // brief_opt.cu
 cudaError_t launch_opt(const OptArgs& a, int n_blocks, cudaStream_t st);
 cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, unsigned char* wpack, cudaStream_t st);

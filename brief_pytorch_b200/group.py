@@ -266,9 +266,10 @@ class SirenGroup:
         return out
 
     def decompress_to_host(self, out_dtype: str = "uint16", host_out: Optional[List[torch.Tensor]] = None,
-                           dev_out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+                           dev_out: Optional[List[torch.Tensor]] = None, post=None) -> List[torch.Tensor]:
         """Decode block by block and overlap every block's device->host copy (copy stream, pinned destination) with the
-        decode of the next one.  Returns the pinned host tensors (uint16 as int16 bit patterns)."""
+        decode of the next one.  `post(i, dev_block)` (optional) runs on the decode stream between block i's decode and
+        its copy (the Decompress.postprocess step).  Returns the pinned host tensors (uint16 as int16 bit patterns)."""
         dt = _DT2TORCH[_NP2DT[out_dtype]]
         n = len(self.specs)
         shapes = [tuple(int(x) for x in s.dims) for s in self.specs]
@@ -280,6 +281,8 @@ class SirenGroup:
         copy = torch.cuda.Stream(device=self.device)
         for i in range(n):
             self.decompress(out_dtype, out=dev_out, nets=[i])
+            if post is not None:
+                post(i, dev_out[i])
             ev = torch.cuda.Event()
             ev.record(main)
             with torch.cuda.stream(copy):
@@ -347,6 +350,35 @@ def volume_quality(a: torch.Tensor, b: torch.Tensor, data_range: float, np_dtype
     mse = out[0] / (d * h * w)
     return {"mse": mse, "psnr": float(-10.0 * np.log10(mse / (data_range * data_range))) if mse > 0 else float("inf"),
             "ssim": out[1] / out[2]}
+
+
+def preprocess_(vol: torch.Tensor, denoise_level, denoise_close, clip_range, np_dtype: Optional[str] = None,
+                scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The reference's preprocess (utils/misc.py:244-254) on a CUDA block [D,H,W] (or [H,W]) IN PLACE: zero the
+    binary opening of (v <= level) under a ones(close) structure (close False: the plain threshold), then clip.
+    uint16 volumes may be held as int16 bit patterns.  Asynchronous on the current stream; returns `vol`."""
+    lib = _cabi.load()
+    assert vol.is_cuda and vol.is_contiguous() and vol.dim() in (2, 3)
+    if np_dtype is None:
+        np_dtype = {torch.uint8: "uint8", torch.int16: "uint16", torch.uint16: "uint16"}[vol.dtype]
+    if vol.dim() == 2:  # image [H,W]: structure close[:2] (utils/misc.py:251)
+        d, (h, w) = 1, (int(x) for x in vol.shape)
+        close = None if denoise_close is False else [1, int(denoise_close[0]), int(denoise_close[1])]
+    else:
+        d, h, w = (int(x) for x in vol.shape)
+        close = None if denoise_close is False else [int(c) for c in denoise_close[:3]]
+    if vol.numel() == 0:
+        return vol
+    need = int(lib.brief_preprocess_scratch_bytes(d, h, w))
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=vol.device)
+    c_close = (C.c_int32 * 3)(*close) if close is not None else None
+    with torch.cuda.device(vol.device):
+        check(lib.brief_preprocess(_ptr(vol), _NP2DT[np_dtype], d, h, w, float(denoise_level), c_close,
+                                   float(clip_range[0]), float(clip_range[1]), _ptr(scratch), vol.device.index or 0,
+                                   _stream(vol.device)))
+    scratch.record_stream(torch.cuda.current_stream(vol.device))
+    return vol
 
 
 def launch_count() -> int:

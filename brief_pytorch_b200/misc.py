@@ -55,6 +55,30 @@ def parse_weight(data: np.ndarray, weight_type_list: Iterable[str]) -> np.ndarra
     return weight
 
 
+def preprocess_is_identity(np_dtype, denoise_level, clip_range) -> bool:
+    """For unsigned data, level <= 0 only ever rewrites zeros with zeros, and a clip to the whole dtype range changes
+    nothing: the shipped configs (level 0, clip [0, 65535]) are this case."""
+    tmax = 255 if np.dtype(np_dtype) == np.uint8 else 65535
+    return np.dtype(np_dtype) in (np.uint8, np.uint16) and denoise_level <= 0 and clip_range[0] <= 0 and clip_range[1] >= tmax
+
+
+def preprocess(data: np.ndarray, denoise_level, denoise_close, clip_range, device="cuda") -> np.ndarray:
+    """Same call as the reference's preprocess (utils/misc.py:244-254) for uint8 / uint16 data [D,H,W,1] / [H,W,1]:
+    the block goes to the device, the threshold + binary opening + clip run there (brief_preprocess, one bit per voxel
+    for the morphology), and the result comes back.  The reference also zeroes its INPUT array in place; this mirror
+    leaves the input untouched (main.py uses the returned array only)."""
+    from .group import preprocess_
+    data = np.asarray(data)
+    if data.dtype not in (np.uint8, np.uint16) or data.shape[-1] != 1 or data.ndim not in (3, 4):
+        raise NotImplementedError("preprocess on the device: uint8 / uint16 data with one channel")
+    _limits(data, clip_range[0], clip_range[1])  # range_limit (utils/tool.py:26-30)
+    flat = np.ascontiguousarray(data[..., 0])
+    t = torch.from_numpy(flat.view(np.int16) if flat.dtype == np.uint16 else flat).to(device)
+    preprocess_(t, denoise_level, denoise_close, clip_range, data.dtype.name)
+    out = t.cpu().numpy()
+    return (out.view(np.uint16) if data.dtype == np.uint16 else out)[..., None]
+
+
 def weight_rules_for_kernel(data: np.ndarray, weight_type_list: Iterable[str]):
     """Translate rule strings into on-chip (lo, hi, scale) triples; returns None when a rule needs the
     explicit weight volume ('exp', or more than 4 rules)."""

@@ -208,6 +208,20 @@ int brief_sample_indices(uint64_t seed, uint64_t step, int32_t net, int64_t batc
 int brief_block_stats(void* const* host_dev_raw, const int64_t* host_sizes, int32_t n_blocks, int32_t dtype,
                       int32_t device, double* host_out, void* stream);
 
+/* Replaces the reference's `preprocess` (utils/misc.py:244-254; called on every block before the fit, main.py:336,
+ * and on every decoded block, main.py:295) on one block [depth][height][width] of uint8 / uint16 voxels in device
+ * memory, IN PLACE and bit for bit:
+ *     v[ binary_opening(v <= level, structure = ones(close[0], close[1], close[2])) ] = 0;  v = clip(v, clip_lo, clip_hi)
+ * host_close == NULL is the reference's `denoise_close == False` (plain threshold, no opening); each close[k] must be
+ * in 1..4.  For a 2-D image [height][width] pass depth = 1 and close = {1, c0, c1} (utils/misc.py:251).  clip_lo /
+ * clip_hi must satisfy 0 <= lo <= hi <= dtype max (the reference's range_limit assertion) else BRIEF_ERR_INVALID.
+ * dev_scratch: brief_preprocess_scratch_bytes(depth, height, width) bytes of device memory (two 1-bit-per-voxel masks).
+ * Asynchronous on `stream`. */
+int64_t brief_preprocess_scratch_bytes(int32_t depth, int32_t height, int32_t width);
+int brief_preprocess(void* dev_volume, int32_t dtype, int32_t depth, int32_t height, int32_t width, double level,
+                     const int32_t* host_close, double clip_lo, double clip_hi, void* dev_scratch, int32_t device,
+                     void* stream);
+
 /* Replaces the reference's deblocking post-filter (deblock.cpp:226-321, its only native component; deblock.py is the
  * float twin) on a decoded uint16 volume [depth][height][width] in device memory, in place, bit for bit:
  * host_blocks holds n_blocks x 6 int32 (z1, z2, y1, y2, x1, x2, inclusive ends — the chunk directory names

@@ -280,6 +280,52 @@ def preprocess(data: np.ndarray, denoise_level: int, denoise_close, clip_range):
     return data.clip(l, h)
 
 
+def box_opening(mask: np.ndarray, size) -> np.ndarray:
+    """What ndimage.binary_opening(mask, structure=np.ones(size), iterations=1) computes, written out: the erosion
+    E[q] = AND of the mask over the box anchored at q (boxes that leave the array are 0: border_value = 0), the opening
+    O[p] = OR of E over all boxes containing p.  Pinned against scipy in oracle/gen_golden_preprocess.py and in
+    tests/test_oracle_golden.py; the device kernel (brief_preprocess.cu) is this on one bit per voxel."""
+    mask = np.asarray(mask, dtype=bool)
+    size = tuple(int(s) for s in size)
+    assert mask.ndim == len(size)
+    er = mask.copy()
+    for ax, s in enumerate(size):      # separable AND over the box, anchored at the low corner
+        acc = er.copy()
+        for k in range(1, s):
+            sh = np.zeros_like(er)
+            sl_dst = [slice(None)] * er.ndim
+            sl_src = [slice(None)] * er.ndim
+            sl_dst[ax], sl_src[ax] = slice(0, max(er.shape[ax] - k, 0)), slice(k, None)
+            sh[tuple(sl_dst)] = er[tuple(sl_src)]
+            acc &= sh                 # positions whose box leaves the array read 0
+        er = acc
+    op = er.copy()
+    for ax, s in enumerate(size):      # separable OR over the anchors whose box contains p
+        acc = op.copy()
+        for k in range(1, s):
+            sh = np.zeros_like(op)
+            sl_dst = [slice(None)] * op.ndim
+            sl_src = [slice(None)] * op.ndim
+            sl_dst[ax], sl_src[ax] = slice(k, None), slice(0, max(op.shape[ax] - k, 0))
+            sh[tuple(sl_dst)] = op[tuple(sl_src)]
+            acc |= sh
+        op = acc
+    return op
+
+
+def preprocess_restated(data: np.ndarray, denoise_level, denoise_close, clip_range) -> np.ndarray:
+    """preprocess without scipy (box_opening above); does not touch its input."""
+    data = np.array(data, copy=True)
+    m = data <= denoise_level
+    if denoise_close is not False:
+        k = tuple(list(denoise_close)[:2] + [1]) if data.ndim == 3 else tuple(list(denoise_close) + [1])
+        m = box_opening(m, k)
+    data[m] = 0
+    l, h = clip_range
+    assert 0 <= l <= h <= get_type_max(data)
+    return data.clip(l, h)
+
+
 # --------------------------------------------------------------------------------------
 # Samplers                                   main.py:38-163 (== utils/sampler.py:9-94)
 # --------------------------------------------------------------------------------------
