@@ -6,12 +6,13 @@
 // scipy.ndimage on the host: a threshold pass, an erosion, a dilation and a fancy-index store, each a full numpy pass
 // over the block.  Here the mask lives as ONE BIT per voxel (32 voxels of an x-row per word), so the morphology is a
 // handful of word ANDs / ORs / funnel shifts per 32 voxels, and the only volume-sized traffic is
-//   pass 1  mask_kernel   read the block once (sizeof(T) B/voxel), write 1 bit/voxel;
+//   pass 1  mask_*_kernel read the block once (sizeof(T) B/voxel), write 1 bit/voxel;
 //   pass 2  open_kernel   bitmask -> opened bitmask (1/16 of the block, L2-resident; skipped for a 1x1x1 structure);
 //   pass 3  apply_kernel  write zeros where the opened bit is set; the block is READ again only when the clip range
 //                         is not the whole dtype range (then every voxel is read, zeroed / clipped and written).
 // Algorithmic bytes per voxel: sizeof(T) read + sizeof(T) written for the voxels that change.  All three are HBM-bound
-// byte kernels: 16-byte vector accesses when the row length allows it (W % (16/sizeof(T)) == 0), scalar otherwise.
+// byte kernels with three row paths: flat (W % 32 == 0: no index arithmetic, warp-coalesced words), vector
+// (W % (16/sizeof(T)) == 0: 16-byte accesses per row) and scalar (any W).
 //
 // Opening with a box structure (what np.ones(close) is): erosion E[q] = AND of the mask over the box anchored at q
 // (boxes leaving the block count as 0 — scipy's border_value = 0), opening O[p] = OR of E over the boxes containing p.
@@ -21,6 +22,26 @@
 namespace brief {
 
 constexpr int kPreThreads = 256;
+
+// Threshold of VPT voxels held in one 16-byte vector -> VPT mask bits.
+template <typename T>
+__device__ __forceinline__ unsigned int vec_threshold(const uint4& q, unsigned int thr) {
+  const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+  unsigned int bits = 0;
+  if (sizeof(T) == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bits |= ((w[i] & 0xffffu) <= thr ? 1u : 0u) << (2 * i);
+      bits |= ((w[i] >> 16) <= thr ? 1u : 0u) << (2 * i + 1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bits |= (((w[i] >> (8 * j)) & 0xffu) <= thr ? 1u : 0u) << (4 * i + j);
+  }
+  return bits;
+}
 
 // ---- pass 1: threshold -> bitmask -------------------------------------------------------------------------------------
 // Mask layout: [D][H][WW] 32-bit words, WW = ceil(W / 32); bit b of word wx <-> x = 32 wx + b; bits with x >= W are 0.
@@ -36,22 +57,41 @@ __global__ void __launch_bounds__(kPreThreads) mask_vec_kernel(const T* __restri
     const long long row = v / vec_per_row;
     const int iv = (int)(v - row * vec_per_row);
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(vol + row * W) + iv);
-    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
-    unsigned int bits = 0;
-    if (sizeof(T) == 2) {
+    const unsigned int bits = vec_threshold<T>(q, thr);
+    if (sizeof(T) == 2) mask[row * WW * 4 + iv] = (unsigned char)bits;
+    else reinterpret_cast<unsigned short*>(mask + row * WW * 4)[iv] = (unsigned short)bits;
+  }
+}
+
+// Rows that are whole mask words (W % 32 == 0, the usual block shapes): volume and mask are both flat, no index
+// arithmetic at all.  One warp = 32 mask words = 1024 voxels per iteration: every lane has LPW independent 16-byte loads
+// in flight, the VPT-bit pieces are assembled into words by butterfly shuffles and stored as one coalesced 128-byte line.
+template <typename T>
+__global__ void __launch_bounds__(kPreThreads) mask_flat_kernel(const uint4* __restrict__ vol, long long nwords,
+                                                                 unsigned int thr, unsigned int* __restrict__ mask) {
+  constexpr int VPT = 16 / sizeof(T), LPW = 32 / VPT, PER = 32 / LPW;  // lanes per word (4 / 2), words per 32 vectors
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long w0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; w0 < nwords; w0 += nwarps * 32) {
+    uint4 q[LPW];
+    bool ok[LPW];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        bits |= ((w[i] & 0xffffu) <= thr ? 1u : 0u) << (2 * i);
-        bits |= ((w[i] >> 16) <= thr ? 1u : 0u) << (2 * i + 1);
-      }
-      mask[row * WW * 4 + iv] = (unsigned char)bits;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bits |= (((w[i] >> (8 * j)) & 0xffu) <= thr ? 1u : 0u) << (4 * i + j);
-      reinterpret_cast<unsigned short*>(mask + row * WW * 4)[iv] = (unsigned short)bits;
+    for (int j = 0; j < LPW; ++j) {
+      const int lv = 32 * j + lane;  // vector within the warp's 32 words
+      ok[j] = w0 + lv / LPW < nwords;
+      if (ok[j]) q[j] = __ldg(vol + w0 * LPW + lv);
     }
+    unsigned int r = 0;
+#pragma unroll
+    for (int j = 0; j < LPW; ++j) {
+      unsigned int x = ok[j] ? vec_threshold<T>(q[j], thr) << (VPT * (lane % LPW)) : 0u;
+      x |= __shfl_xor_sync(0xffffffffu, x, 1);
+      if (LPW == 4) x |= __shfl_xor_sync(0xffffffffu, x, 2);
+      // every lane of a group now holds word PER * j + lane / LPW; lane k takes word k
+      const unsigned int t = __shfl_sync(0xffffffffu, x, (lane % PER) * LPW);
+      if (lane / PER == j) r = t;
+    }
+    if (w0 + lane < nwords) mask[w0 + lane] = r;
   }
 }
 
@@ -72,69 +112,89 @@ __global__ void __launch_bounds__(kPreThreads) mask_scalar_kernel(const T* __res
 }
 
 // ---- pass 2: opening on the bitmask ---------------------------------------------------------------------------------------
-// x-erosion of one row around word wx: bit (32 + b) of the result <-> E_x at x = 32 wx + b, bit b <-> x = 32 (wx-1) + b.
-template <int SX>
-__device__ __forceinline__ unsigned long long row_erode_x(const unsigned int* __restrict__ m, int z, int y, int wx, int D,
-                                                          int H, int WW) {
-  if (z < 0 || z >= D || y < 0 || y >= H) return 0ull;
-  const unsigned int* r = m + ((long long)z * H + y) * WW;
-  const unsigned int p = wx > 0 ? __ldg(r + wx - 1) : 0u, c = __ldg(r + wx), n = wx + 1 < WW ? __ldg(r + wx + 1) : 0u;
-  const unsigned long long lo = (unsigned long long)p | ((unsigned long long)c << 32);
-  unsigned long long e = lo;
-#pragma unroll
-  for (int k = 1; k < SX; ++k) e &= (lo >> k) | ((unsigned long long)n << (64 - k));
-  return e;
-}
-
+// One thread = one mask word column (z, wx) over `yr` consecutive rows.  Per row it x-erodes the words of the 2 SZ - 1
+// planes around z (64-bit window: bit 32 + b <-> x = 32 wx + b, bit b <-> x = 32 (wx - 1) + b), ANDs them over z for the SZ
+// box anchors, and slides the result through a register window of 2 SY - 1 rows: each output word costs (2 SZ - 1) x 3
+// word loads instead of (2 SZ - 1)(2 SY - 1) x 3.  Plane pointers and all the z / x border predicates are loop-invariant.
 template <int SZ, int SY, int SX>
-__global__ void __launch_bounds__(kPreThreads) open_kernel(const unsigned int* __restrict__ m, int D, int H, int WW,
+__global__ void __launch_bounds__(kPreThreads) open_kernel(const unsigned int* __restrict__ m, int D, int H, int WW, int yr,
                                                            unsigned int* __restrict__ out) {
-  const long long total = (long long)D * H * WW;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int wx = (int)(i % WW);
-    const long long zy = i / WW;
-    const int y = (int)(zy % H), z = (int)(zy / H);
-    // E[zq][yq] for the SZ x SY box anchors (zq, yq) in [z-SZ+1, z] x [y-SY+1, y] whose boxes contain (z, y)
-    unsigned long long E[SZ][SY];
+  constexpr int NP = 2 * SZ - 1, NR = 2 * SY - 1;
+  const unsigned int ygroups = (unsigned int)((H + yr - 1) / yr);
+  const unsigned int total = (unsigned int)D * ygroups * (unsigned int)WW;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int wx = (int)(i % (unsigned int)WW);
+    const unsigned int t = i / (unsigned int)WW;
+    const int y0 = (int)(t % ygroups) * yr, z = (int)(t / ygroups);
+    const bool has_p = wx > 0, has_n = wx + 1 < WW;
+    // word (z', 0, wx) of the planes z - (SZ-1) .. z + (SZ-1).  Planes, rows and neighbour words outside the block are
+    // read from a clamped (valid) address and masked to 0 afterwards: every load of a row is unconditional, so all
+    // 3 (2 SZ - 1) of them are in flight together instead of one guarded group after the other.
+    const unsigned int* plane[NP];
+    unsigned long long zmask[NP];
 #pragma unroll
-    for (int a = 0; a < SZ; ++a)
+    for (int k = 0; k < NP; ++k) {
+      const int zz = z - (SZ - 1) + k;
+      plane[k] = m + (size_t)min(max(zz, 0), D - 1) * H * WW + wx;
+      zmask[k] = (zz >= 0 && zz < D) ? ~0ull : 0ull;
+    }
+    const int dp = has_p ? -1 : 0, dn = has_n ? 1 : 0;
+    const unsigned int pm = has_p ? ~0u : 0u, nm = has_n ? ~0u : 0u;
+    // R[a] of row y: AND over the SZ planes of box anchor a of the x-eroded words; 0 for rows outside the block
+    auto load_row = [&](int y, unsigned long long (&R)[SZ]) {
+      unsigned long long X[NP];
+      const unsigned long long ymask = (y >= 0 && y < H) ? ~0ull : 0ull;
+      const int off = min(max(y, 0), H - 1) * WW;
+      unsigned int c[NP], pw[NP], nw[NP];
 #pragma unroll
-      for (int b = 0; b < SY; ++b) E[a][b] = ~0ull;
+      for (int k = 0; k < NP; ++k) {
+        const unsigned int* r = plane[k] + off;
+        c[k] = __ldg(r);
+        pw[k] = __ldg(r + dp);
+        nw[k] = __ldg(r + dn);
+      }
 #pragma unroll
-    for (int dz = -(SZ - 1); dz <= SZ - 1; ++dz) {
-      // y-erosion of plane z + dz for the SY anchors
-      unsigned long long Y[SY];
+      for (int k = 0; k < NP; ++k) {
+        const unsigned int n = nw[k] & nm;
+        const unsigned long long lo = (unsigned long long)(pw[k] & pm) | ((unsigned long long)c[k] << 32);
+        unsigned long long e = lo;
 #pragma unroll
-      for (int b = 0; b < SY; ++b) Y[b] = ~0ull;
-#pragma unroll
-      for (int dy = -(SY - 1); dy <= SY - 1; ++dy) {
-        const unsigned long long X = row_erode_x<SX>(m, z + dz, y + dy, wx, D, H, WW);
-#pragma unroll
-        for (int b = 0; b < SY; ++b) {  // anchor yq = y - (SY-1) + b covers rows yq .. yq + SY - 1
-          const int off = dy + (SY - 1) - b;
-          if (off >= 0 && off < SY) Y[b] &= X;
-        }
+        for (int s = 1; s < SX; ++s) e &= (lo >> s) | ((unsigned long long)n << (64 - s));
+        X[k] = e & zmask[k] & ymask;
       }
 #pragma unroll
       for (int a = 0; a < SZ; ++a) {
-        const int off = dz + (SZ - 1) - a;
-        if (off >= 0 && off < SZ) {
+        R[a] = X[a];
 #pragma unroll
-          for (int b = 0; b < SY; ++b) E[a][b] &= Y[b];
-        }
+        for (int s = 1; s < SZ; ++s) R[a] &= X[a + s];
       }
+    };
+    unsigned long long R[NR][SZ];  // window rows y - (SY-1) .. y + (SY-1)
+#pragma unroll
+    for (int k = 1; k < NR; ++k) load_row(y0 - SY + k, R[k]);
+    const int y_end = min(y0 + yr, H);
+    unsigned int* o = out + ((size_t)z * H + y0) * WW + wx;
+    for (int y = y0; y < y_end; ++y, o += WW) {
+#pragma unroll
+      for (int k = 0; k < NR - 1; ++k)
+#pragma unroll
+        for (int a = 0; a < SZ; ++a) R[k][a] = R[k + 1][a];
+      load_row(y + SY - 1, R[NR - 1]);
+      unsigned long long T = 0ull;
+#pragma unroll
+      for (int b = 0; b < SY; ++b)  // box anchor row y - (SY-1) + b covers window rows b .. b + SY - 1
+#pragma unroll
+        for (int a = 0; a < SZ; ++a) {
+          unsigned long long e = R[b][a];
+#pragma unroll
+          for (int j = 1; j < SY; ++j) e &= R[b + j][a];
+          T |= e;
+        }
+      unsigned long long O = T;  // x-dilation: O[x] = OR_s E[x - s]
+#pragma unroll
+      for (int s = 1; s < SX; ++s) O |= T << s;
+      *o = (unsigned int)(O >> 32);
     }
-    unsigned long long T = 0ull;
-#pragma unroll
-    for (int a = 0; a < SZ; ++a)
-#pragma unroll
-      for (int b = 0; b < SY; ++b) T |= E[a][b];
-    // x-dilation: O[x] = OR_k E[x - k]
-    unsigned long long O = T;
-#pragma unroll
-    for (int k = 1; k < SX; ++k) O |= T << k;
-    out[i] = (unsigned int)(O >> 32);
   }
 }
 
@@ -142,6 +202,41 @@ __global__ void __launch_bounds__(kPreThreads) open_kernel(const unsigned int* _
 template <typename T>
 __device__ __forceinline__ unsigned int clip1(unsigned int v, unsigned int lo, unsigned int hi) {
   return min(max(v, lo), hi);
+}
+
+template <typename T, bool CLIP>
+__device__ __forceinline__ void apply_vec(uint4* p, unsigned int bits, unsigned int lo, unsigned int hi) {
+  constexpr int VPT = 16 / sizeof(T);
+  if (!CLIP) {
+    if (bits == 0) return;
+    if (bits == (1u << VPT) - 1u) { *p = make_uint4(0, 0, 0, 0); return; }
+  }
+  const uint4 q = *p;
+  unsigned int w[4] = {q.x, q.y, q.z, q.w};
+  if (sizeof(T) == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      unsigned int a = w[i] & 0xffffu, b = w[i] >> 16;
+      if (bits & (1u << (2 * i))) a = 0;
+      if (bits & (1u << (2 * i + 1))) b = 0;
+      if (CLIP) { a = clip1<T>(a, lo, hi); b = clip1<T>(b, lo, hi); }
+      w[i] = a | (b << 16);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      unsigned int r = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        unsigned int a = (w[i] >> (8 * j)) & 0xffu;
+        if (bits & (1u << (4 * i + j))) a = 0;
+        if (CLIP) a = clip1<T>(a, lo, hi);
+        r |= a << (8 * j);
+      }
+      w[i] = r;
+    }
+  }
+  *p = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 template <typename T, bool CLIP>
@@ -158,37 +253,28 @@ __global__ void __launch_bounds__(kPreThreads) apply_vec_kernel(T* __restrict__ 
     unsigned int bits;
     if (sizeof(T) == 2) bits = mask[row * WW * 4 + iv];
     else bits = reinterpret_cast<const unsigned short*>(mask + row * WW * 4)[iv];
-    uint4* p = reinterpret_cast<uint4*>(vol + row * W) + iv;
-    if (!CLIP) {
-      if (bits == 0) continue;
-      if (bits == (1u << VPT) - 1u) { *p = make_uint4(0, 0, 0, 0); continue; }
+    apply_vec<T, CLIP>(reinterpret_cast<uint4*>(vol + row * W) + iv, bits, lo, hi);
+  }
+}
+
+// flat twin of mask_flat_kernel: one coalesced 128-byte load of 32 mask words per warp, the VPT-bit pieces handed to the
+// lanes by shuffle, LPW coalesced 512-byte stores.
+template <typename T, bool CLIP>
+__global__ void __launch_bounds__(kPreThreads) apply_flat_kernel(uint4* __restrict__ vol, long long nwords,
+                                                                  const unsigned int* __restrict__ mask, unsigned int lo,
+                                                                  unsigned int hi) {
+  constexpr int VPT = 16 / sizeof(T), LPW = 32 / VPT;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long w0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; w0 < nwords; w0 += nwarps * 32) {
+    const unsigned int word = w0 + lane < nwords ? __ldg(mask + w0 + lane) : 0u;
+    if (!CLIP && __ballot_sync(0xffffffffu, word != 0) == 0) continue;
+#pragma unroll
+    for (int j = 0; j < LPW; ++j) {
+      const int lv = 32 * j + lane;
+      const unsigned int bits = (__shfl_sync(0xffffffffu, word, lv / LPW) >> (VPT * (lv % LPW))) & ((1u << VPT) - 1u);
+      if (w0 + lv / LPW < nwords) apply_vec<T, CLIP>(vol + w0 * LPW + lv, bits, lo, hi);
     }
-    uint4 q = *p;
-    unsigned int w[4] = {q.x, q.y, q.z, q.w};
-    if (sizeof(T) == 2) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        unsigned int a = w[i] & 0xffffu, b = w[i] >> 16;
-        if (bits & (1u << (2 * i))) a = 0;
-        if (bits & (1u << (2 * i + 1))) b = 0;
-        if (CLIP) { a = clip1<T>(a, lo, hi); b = clip1<T>(b, lo, hi); }
-        w[i] = a | (b << 16);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        unsigned int r = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          unsigned int a = (w[i] >> (8 * j)) & 0xffu;
-          if (bits & (1u << (4 * i + j))) a = 0;
-          if (CLIP) a = clip1<T>(a, lo, hi);
-          r |= a << (8 * j);
-        }
-        w[i] = r;
-      }
-    }
-    *p = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -223,23 +309,24 @@ size_t preprocess_scratch_bytes(int D, int H, int W) {
 }
 
 template <int SZ, int SY>
-static bool open_dispatch_x(int sx, const unsigned int* m, int D, int H, int WW, unsigned int* out, int grid, cudaStream_t st) {
+static bool open_dispatch_x(int sx, const unsigned int* m, int D, int H, int WW, int yr, unsigned int* out, int grid,
+                            cudaStream_t st) {
   switch (sx) {
-    case 1: open_kernel<SZ, SY, 1><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, out); return true;
-    case 2: open_kernel<SZ, SY, 2><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, out); return true;
-    case 3: open_kernel<SZ, SY, 3><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, out); return true;
-    case 4: open_kernel<SZ, SY, 4><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, out); return true;
+    case 1: open_kernel<SZ, SY, 1><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, yr, out); return true;
+    case 2: open_kernel<SZ, SY, 2><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, yr, out); return true;
+    case 3: open_kernel<SZ, SY, 3><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, yr, out); return true;
+    case 4: open_kernel<SZ, SY, 4><<<grid, kPreThreads, 0, st>>>(m, D, H, WW, yr, out); return true;
   }
   return false;
 }
 template <int SZ>
-static bool open_dispatch_y(int sy, int sx, const unsigned int* m, int D, int H, int WW, unsigned int* out, int grid,
-                            cudaStream_t st) {
+static bool open_dispatch_y(int sy, int sx, const unsigned int* m, int D, int H, int WW, int yr, unsigned int* out,
+                            int grid, cudaStream_t st) {
   switch (sy) {
-    case 1: return open_dispatch_x<SZ, 1>(sx, m, D, H, WW, out, grid, st);
-    case 2: return open_dispatch_x<SZ, 2>(sx, m, D, H, WW, out, grid, st);
-    case 3: return open_dispatch_x<SZ, 3>(sx, m, D, H, WW, out, grid, st);
-    case 4: return open_dispatch_x<SZ, 4>(sx, m, D, H, WW, out, grid, st);
+    case 1: return open_dispatch_x<SZ, 1>(sx, m, D, H, WW, yr, out, grid, st);
+    case 2: return open_dispatch_x<SZ, 2>(sx, m, D, H, WW, yr, out, grid, st);
+    case 3: return open_dispatch_x<SZ, 3>(sx, m, D, H, WW, yr, out, grid, st);
+    case 4: return open_dispatch_x<SZ, 4>(sx, m, D, H, WW, yr, out, grid, st);
   }
   return false;
 }
@@ -258,8 +345,13 @@ static cudaError_t preprocess_t(T* vol, int D, int H, int W, unsigned int thr, b
   auto grid_for = [&](long long items, int per_cta) { return (int)std::max<long long>(1, std::min<long long>(cap, (items + per_cta - 1) / per_cta)); };
   *launches = 0;
   const unsigned int* final_mask = nullptr;
+  if (words >= (1ll << 32)) return cudaErrorInvalidValue;  // 2^37 voxels per block: far beyond any 180 GB device
+  const bool flat = vec && (W % 32 == 0);
   if (any_mask) {
-    if (vec) {
+    if (flat) {
+      mask_flat_kernel<T><<<grid_for(words, kPreThreads), kPreThreads, 0, st>>>(reinterpret_cast<const uint4*>(vol), words, thr,
+                                                                               mask);
+    } else if (vec) {
       cudaError_t e = cudaMemsetAsync(mask, 0, words * sizeof(unsigned int), st);  // row tails past W/VPT vectors stay 0
       if (e != cudaSuccess) return e;
       mask_vec_kernel<T><<<grid_for(rows * (W / VPT), kPreThreads), kPreThreads, 0, st>>>(
@@ -270,13 +362,16 @@ static cudaError_t preprocess_t(T* vol, int D, int H, int W, unsigned int thr, b
     ++*launches;
     final_mask = mask;
     if (sz * sy * sx > 1) {
-      const int grid = grid_for(words, kPreThreads);
+      // rows per thread: 8 when that still leaves two full waves of threads, fewer for small blocks
+      int yr = 8;
+      while (yr > 1 && (long long)D * ((H + yr - 1) / yr) * WW < 2ll * num_sms * 2048) yr >>= 1;
+      const int grid = grid_for((long long)D * ((H + yr - 1) / yr) * WW, kPreThreads);
       bool ok = false;
       switch (sz) {
-        case 1: ok = open_dispatch_y<1>(sy, sx, mask, D, H, WW, opened, grid, st); break;
-        case 2: ok = open_dispatch_y<2>(sy, sx, mask, D, H, WW, opened, grid, st); break;
-        case 3: ok = open_dispatch_y<3>(sy, sx, mask, D, H, WW, opened, grid, st); break;
-        case 4: ok = open_dispatch_y<4>(sy, sx, mask, D, H, WW, opened, grid, st); break;
+        case 1: ok = open_dispatch_y<1>(sy, sx, mask, D, H, WW, yr, opened, grid, st); break;
+        case 2: ok = open_dispatch_y<2>(sy, sx, mask, D, H, WW, yr, opened, grid, st); break;
+        case 3: ok = open_dispatch_y<3>(sy, sx, mask, D, H, WW, yr, opened, grid, st); break;
+        case 4: ok = open_dispatch_y<4>(sy, sx, mask, D, H, WW, yr, opened, grid, st); break;
       }
       if (!ok) return cudaErrorInvalidValue;
       ++*launches;
@@ -289,7 +384,12 @@ static cudaError_t preprocess_t(T* vol, int D, int H, int W, unsigned int thr, b
     if (e != cudaSuccess) return e;
     final_mask = mask;
   }
-  if (vec) {
+  if (flat) {
+    const int grid = grid_for(words, kPreThreads);
+    uint4* v4 = reinterpret_cast<uint4*>(vol);
+    if (clip) apply_flat_kernel<T, true><<<grid, kPreThreads, 0, st>>>(v4, words, final_mask, lo, hi);
+    else apply_flat_kernel<T, false><<<grid, kPreThreads, 0, st>>>(v4, words, final_mask, lo, hi);
+  } else if (vec) {
     const int grid = grid_for(rows * (W / VPT), kPreThreads);
     const unsigned char* mb = reinterpret_cast<const unsigned char*>(final_mask);
     if (clip) apply_vec_kernel<T, true><<<grid, kPreThreads, 0, st>>>(vol, rows, W, WW, mb, lo, hi);
