@@ -99,7 +99,8 @@ struct BriefGroup {
   size_t total_wpack = 0;
   DevBuf<NetDev> d_nets;
   DevBuf<float> d_params, d_grads, d_m, d_v, d_axes, d_partials, d_loss_partials, d_loss_scratch;
-  DevBuf<unsigned char> d_wpack;
+  DevBuf<unsigned char> d_wpack, d_stash;
+  size_t stash_stride = 0;  // wide tensor-core fit kernel: activation stash bytes per CTA
   DevBuf<int> d_fit_tables, d_eval_tables;
   DevBuf<void*> d_outptrs;
   bool nets_dirty = true;   // host NetDev array differs from the device copy
@@ -316,6 +317,13 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   tb.add(g->opt, op, on);
   RC(upload_tables(g->d_fit_tables, tb.tab, st));
   CU(g->d_partials.ensure((size_t)part_total));
+  // wide tensor-core buckets: one activation stash per CTA (buckets launch one after the other and share it)
+  size_t stash_total = 0;
+  g->stash_stride = 0;
+  for (int b = 5; b < kBuckets; ++b)
+    if (g->tc_fit[b].blocks > 0) g->stash_stride = std::max(g->stash_stride, tc_fit_stash_bytes(16 * b, g->tc_L[b]));
+  for (int b = 5; b < kBuckets; ++b) stash_total = std::max(stash_total, (size_t)g->tc_fit[b].blocks * g->stash_stride);
+  if (stash_total > 0) CU(g->d_stash.ensure(stash_total));
   CU(g->d_loss_partials.ensure((size_t)slice_total));
   CU(g->d_loss_scratch.ensure((size_t)g->n_nets));
   g->nets_dirty = true;
@@ -343,6 +351,8 @@ int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uin
   a.partials = g->d_partials.p;
   a.loss_partials = g->d_loss_partials.p;
   a.wpack = g->d_wpack.p;
+  a.stash = g->d_stash.p;
+  a.stash_stride = g->stash_stride;
   if (g->simt_fit.blocks > 0) {
     a.work_prefix = g->d_fit_tables.p + g->simt_fit.off_prefix;
     a.work_net = g->d_fit_tables.p + g->simt_fit.off_net;
@@ -544,7 +554,7 @@ void brief_group_destroy(BriefGroup* g) {
   cudaSetDevice(g->device);
   g->d_nets.release(); g->d_params.release(); g->d_grads.release(); g->d_m.release(); g->d_v.release();
   g->d_axes.release(); g->d_partials.release(); g->d_loss_partials.release(); g->d_loss_scratch.release();
-  g->d_wpack.release(); g->d_fit_tables.release(); g->d_eval_tables.release(); g->d_outptrs.release();
+  g->d_wpack.release(); g->d_stash.release(); g->d_fit_tables.release(); g->d_eval_tables.release(); g->d_outptrs.release();
   delete g;
 }
 

@@ -47,6 +47,8 @@ struct FitArgs {
   float* partials;       // per-slice gradient slots (padded device layout)
   float* loss_partials;  // per-slice loss terms
   const unsigned char* wpack;
+  unsigned char* stash;     // wide tensor-core kernel: per-CTA activation stash (stash_stride bytes per CTA)
+  size_t stash_stride;
 };
 
 // Optimiser step over the whole group (one launch).
@@ -111,6 +113,7 @@ cudaError_t launch_pack(const NetDev* nets, int n_nets, const float* params, uns
 bool tc_supported(int f, int L, int in_dim, int out_dim);
 int tc_fpad(int f);
 int tc_fit_ctas_per_sm(int F_PAD, int L);
+size_t tc_fit_stash_bytes(int F_PAD, int L);  // wide kernel (F_PAD > 64): activation stash per CTA, else 0
 size_t tc_wpack_bytes(int F_PAD, int L);
 size_t tc_eval_smem(int F_PAD, int L);
 int tc_eval_groups(int F_PAD, int L);

@@ -914,6 +914,359 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 }
 
 // ==================================================================================================================
+// fit, wide networks (64 < F_PAD <= 128: hipct 256^3 blocks, f = 113)
+// ==================================================================================================================
+// At these widths nothing of the narrow kernel's residency survives: one layer's weights are 32 KB (the image of an
+// L = 7 network 168 KB), one tile's activations 32 KB per layer, one layer's dW accumulator 128 TMEM columns.  So the
+// wide kernel keeps only WORKING SETS on chip and streams the rest through L2, one 128-sample tile at a time:
+//   * weights:      two [F x F] buffers; layer l lives in buffer (l-1) & 1, fetched by bulk (TMA) copies two stages
+//                   ahead in the forward pass and one stage ahead in the backward pass (the backward pass ends with
+//                   W_1, W_2 resident — exactly what the next tile's forward pass starts with);
+//   * activations:  two [128 x F] buffers (a_j in buffer j & 1).  The forward epilogue also writes a_j (j <= NH-2) in
+//                   operand layout to a per-CTA STASH in global memory (L2-resident: 4 x 32 KB per CTA), from where
+//                   the backward pass brings it back with one bulk copy per stage;
+//   * dW:           ONE accumulator (F columns, M = 128: lane = input feature, column = output feature, so that a warp
+//                   drains 32 consecutive floats of a weight row): computed per tile and per layer, drained with
+//                   red.global.add.f32 into the slice's partial slot (fp32; one CTA per slot and a fixed tile order,
+//                   so the sum is deterministic).  That drain (~3.4 KB per sample through the L2 atomic units) is the
+//                   price of not having 768 TMEM columns.
+// Two threads per sample row (column halves), stages run back to back with CTA barriers: the MMA of a stage, its
+// epilogue and the drain are not overlapped with each other (only the bulk copies run ahead).  Same numerics as the
+// narrow kernel (fp16 operands, fp32 accumulation, hi/lo layer 0, kGradScale).
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// D[128 x N] = A^T B over the tile's 128 samples (both operands MN-major, K = samples); rows past the operand's width
+// read whatever follows the buffer and are ignored by the drain
+template <int N>
+__device__ __forceinline__ void issue_dw128(uint32_t d, uint32_t a_buf, uint32_t b_buf) {
+  constexpr uint32_t idesc = make_idesc(128, N, true, true);
+#pragma unroll
+  for (int k = 0; k < kTile / 16; ++k)
+    mma_f16(d, make_desc(a_buf + k * 2 * 128, 128, kActLBO), make_desc(b_buf + k * 2 * 128, 128, kActLBO), idesc, k > 0);
+}
+
+constexpr int kWideThreads = 256;
+__host__ __device__ constexpr size_t wide_resident_bytes(int F, int NH) { return img_bytes(F, NH) - img_l0_off(F, NH); }
+
+template <int F>
+__global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a) {
+  constexpr int NC = F / 16;
+  constexpr uint32_t BUF = kTile * F * 2, BLK = kTile * 16 * 2;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ NetDev sn;
+  __shared__ __align__(8) uint64_t bar_res, bar_mma, bar_dw, bar_w[2], bar_act[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float4 s_g[kTile];
+  __shared__ float s_gw[kTile];
+  __shared__ float s_y[2][kTile];
+  __shared__ float s_red[4];
+
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;
+  const int c_lo = cg ? (NC + 1) / 2 : 0, c_hi = cg ? NC : (NC + 1) / 2;  // this thread's 16-column chunks
+  const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
+  const int net_id = a.work_net[wi];
+  const int slice = blockIdx.x - a.work_prefix[wi];
+  tc_load_net(sn, a.nets[net_id]);
+  if (t == 0) {
+    mbar_init(&bar_res, 1);
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_dw, 1);
+    mbar_init(&bar_w[0], 1);
+    mbar_init(&bar_w[1], 1);
+    mbar_init(&bar_act[0], 1);
+    mbar_init(&bar_act[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const NetDev& n = sn;
+  const int NH = n.L - 2, f = n.f, F4 = n.F4;
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  unsigned char* sA = smem;             // a_j in sA + (j & 1) * BUF
+  unsigned char* sDz = sA + 2 * BUF;    // dz_l in sDz + ((NH - l) & 1) * BUF
+  unsigned char* sWt = sDz + 2 * BUF;   // W_l in sWt + ((l - 1) & 1) * BUF
+  unsigned char* sX = sWt + 2 * BUF;
+  unsigned char* sDY = sX + BLK;
+  unsigned char* sRes = sDY + BLK;      // layer-0 block | last block | fp32 side block of the image
+  const float* side = reinterpret_cast<const float*>(sRes + (img_side_off(F, NH) - img_l0_off(F, NH)));
+  const float* s_wl = side + 4 * F + NH * F;
+  const float* s_bl = s_wl + F;
+  const unsigned char* img = a.wpack + n.wpack_off;
+  if (t == 0) {
+    const uint32_t bytes = (uint32_t)wide_resident_bytes(F, NH);
+    mbar_expect_tx(&bar_res, bytes);
+    bulk_g2s(sRes, img + img_l0_off(F, NH), bytes, &bar_res);
+  }
+  if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
+  float* part = a.partials + n.part_off + (long long)slice * n.P_dev;
+  for (int i = t; i < (n.P_dev >> 2); i += kWideThreads) reinterpret_cast<float4*>(part)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned char* stash = a.stash + (size_t)blockIdx.x * a.stash_stride;  // a_j (j <= NH-2) at stash + j * BUF
+
+  const uint32_t tm = tmem_base_s;
+  const uint32_t TZ = tm, TXB = tm + F, TDW = tm + 2 * F;
+  const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+  const uint32_t aA = smem_u32(sA), aDz = smem_u32(sDz), aWt = smem_u32(sWt), aX = smem_u32(sX), aDY = smem_u32(sDY),
+                 aL0 = smem_u32(sRes);
+  const float wh = n.wh, w0 = n.w0;
+  const long long s_begin = (long long)slice * n.slice_len;
+  const long long s_end = min((long long)n.batch, s_begin + n.slice_len);
+  const int n_tiles = (int)((s_end - s_begin + kTile - 1) / kTile);
+  const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
+  const float unscale = 2.0f * inv_count / kGradScale;
+  float loss_acc = 0.f;
+  uint32_t ph_mma = 0, ph_dw = 0;
+  // warp 0 only (kept warp-uniform): phase and "copy in flight" of the weight / activation buffers
+  uint32_t ph_w[2] = {0, 0}, ph_act[2] = {0, 0};
+  bool pend_w[2] = {false, false}, pend_act[2] = {false, false};
+
+  auto cta_sync = [&]() {  // operand rows written / TMEM read -> the next stage's MMAs and bulk copies may touch them
+    tc_fence_before();
+    fence_async_all();
+    __syncthreads();
+    tc_fence_after();
+  };
+  auto load_w = [&](int l) {  // warp 0: W_l -> its buffer
+    const int b = (l - 1) & 1;
+    if (elect_one()) {
+      mbar_expect_tx(&bar_w[b], (uint32_t)F * F * 2);
+      bulk_g2s(sWt + (size_t)b * BUF, img + (size_t)(l - 1) * F * F * 2, (uint32_t)F * F * 2, &bar_w[b]);
+    }
+    __syncwarp();
+    pend_w[b] = true;
+  };
+  auto need_w = [&](int l) {
+    const int b = (l - 1) & 1;
+    if (pend_w[b]) { mbar_wait(&bar_w[b], ph_w[b]); ph_w[b] ^= 1; pend_w[b] = false; }
+  };
+  auto load_act = [&](int j) {  // warp 0: a_j from the stash -> its buffer
+    const int b = j & 1;
+    if (elect_one()) {
+      mbar_expect_tx(&bar_act[b], BUF);
+      bulk_g2s(sA + (size_t)b * BUF, stash + (size_t)j * BUF, BUF, &bar_act[b]);
+    }
+    __syncwarp();
+    pend_act[b] = true;
+  };
+  auto need_act = [&](int j) {
+    const int b = j & 1;
+    if (pend_act[b]) { mbar_wait(&bar_act[b], ph_act[b]); ph_act[b] ^= 1; pend_act[b] = false; }
+  };
+  auto wait_mma = [&]() { mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1; tc_fence_after(); };
+  auto wait_dw = [&]() { mbar_wait(&bar_dw, ph_dw); ph_dw ^= 1; tc_fence_after(); };
+  constexpr uint32_t idesc_f = make_idesc(128, F, false, false);
+  auto layer0 = [&]() {  // theta_0 = A0 [128 x 16] * B0^T
+    mma_f16(TZ, make_desc(aX, kActLBO, 128), make_desc(aL0, (F / 8) * 128, 128), idesc_f, 0);
+  };
+
+  if (warp == 0 && n_tiles > 0) {
+    if (NH >= 1) load_w(1);
+    if (NH >= 2) load_w(2);
+  }
+  mbar_wait(&bar_res, 0);
+  __syncthreads();
+
+  for (int k = 0; k < n_tiles; ++k) {
+    // ---- sampler (main.py:126-163 / whole-block cube): one row per thread of the first column group
+    if (cg == 0) {
+      const long long s = s_begin + (long long)k * kTile + r;
+      const bool ok = s < s_end;
+      long long v = 0;
+      if (ok) {
+        if (n.mode == 0) v = s;
+        else if (a.idx) v = a.idx[n.idx_off + s];
+        else v = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
+      }
+      const float raw = brief_raw_value(n, v);
+      float x0, x1, x2;
+      brief_coords(n, a.axes, v, x0, x1, x2);
+      const float yv = ok ? brief_normalize(n, raw) : 0.f;
+      s_gw[r] = ok ? brief_weight(n, v, raw) : 0.f;
+      if (!ok) { x0 = 0.f; x1 = 0.f; x2 = 0.f; }
+      s_g[r] = make_float4(x0, x1, x2, yv);
+      // layer-0 operand row [x_hi(3) 1 x_lo(3) 1 | x_hi(3) 0 0 0 0 0]; also the B operand of dW0
+      const float h0 = __half2float(__float2half_rn(x0)), h1 = __half2float(__float2half_rn(x1)),
+                  h2 = __half2float(__float2half_rn(x2));
+      const uint32_t p01 = pack_f16x2(h0, h1), p21 = pack_f16x2(h2, 1.0f);
+      *reinterpret_cast<uint4*>(sX + chunk_off(r, 0, kTile)) =
+          make_uint4(p01, p21, pack_f16x2(x0 - h0, x1 - h1), pack_f16x2(x2 - h2, 1.0f));
+      *reinterpret_cast<uint4*>(sX + chunk_off(r, 1, kTile)) = make_uint4(p01, pack_f16x2(h2, 0.f), 0u, 0u);
+    }
+    cta_sync();
+    const float4 xf = s_g[r];
+
+    // ---- forward: stage j computes theta_j (TZ) and a_j
+    float ypart = 0.f;
+    for (int j = 0; j <= NH; ++j) {
+      if (warp == 0) {
+        if (j >= 1) need_w(j);
+        if (elect_one()) {
+          if (j == 0) layer0();
+          else issue_forward<F>(TZ, aA + (uint32_t)((j - 1) & 1) * BUF, aWt + (uint32_t)((j - 1) & 1) * BUF);
+          commit(&bar_mma);
+        }
+        __syncwarp();
+      }
+      wait_mma();
+      if (warp == 0 && j >= 1 && j + 2 <= NH) load_w(j + 2);  // the buffer of W_j is free again
+      unsigned char* dst = sA + (size_t)(j & 1) * BUF;
+      unsigned char* gst = stash + (size_t)j * BUF;
+      const bool to_stash = j <= NH - 2;
+      for (int c = c_lo; c < c_hi; ++c) {
+        float v[16];
+        tmem_ld16(TZ + lane_base + 16 * c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fast_sin(v[i]);
+        const uint4 lo4 = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+        const uint4 hi4 = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+        const uint32_t o0 = chunk_off(r, 2 * c, kTile), o1 = chunk_off(r, 2 * c + 1, kTile);
+        *reinterpret_cast<uint4*>(dst + o0) = lo4;
+        *reinterpret_cast<uint4*>(dst + o1) = hi4;
+        if (to_stash) {
+          *reinterpret_cast<uint4*>(gst + o0) = lo4;
+          *reinterpret_cast<uint4*>(gst + o1) = hi4;
+        }
+        if (j == NH) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ypart = fmaf(s_wl[16 * c + i], v[i], ypart);
+        }
+      }
+      if (j == NH) s_y[cg][r] = ypart;
+      cta_sync();
+    }
+
+    // ---- loss (datal2, main.py:176-182), scaled output gradient, dz_NH (theta_NH is still in TZ)
+    const float y = s_bl[0] + s_y[0][r] + s_y[1][r];
+    float dys = 0.f;
+    if (s_begin + (long long)k * kTile + r < s_end) {
+      const float e = y - xf.w;
+      const float wt = (n.tau != 0.f && y <= n.tau) ? 1.0f : s_gw[r];
+      if (cg == 0) loss_acc = fmaf(wt * e, e, loss_acc);
+      dys = kGradScale * wt * e;
+    }
+    if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
+    dys *= wh;
+    for (int c = c_lo; c < c_hi; ++c) {
+      float v[16];
+      tmem_ld16(TZ + lane_base + 16 * c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = dys * s_wl[16 * c + i] * fast_cos(v[i]);
+      store_chunk16_both<true>(sDz, r, c, v, false, 0);
+    }
+    cta_sync();
+    // dWlast (+ dblast in row f): a_NH^T dY
+    if (warp == 0) {
+      if (elect_one()) {
+        issue_dw128<16>(TDW, aA + (uint32_t)(NH & 1) * BUF, aDY);
+        commit(&bar_dw);
+      }
+      __syncwarp();
+    }
+    wait_dw();
+    if (warp == 0 && NH >= 2) load_act(NH - 2);  // into the buffer of a_NH, which dWlast has consumed
+    if (cg == 0) {
+      float v[16];
+      tmem_ld16(TDW + lane_base, v);
+      tmem_ld_wait();
+      if (r < f) red_add_f32(part + dl_Wlast(n) + r, v[0] * unscale);
+      else if (r == f) red_add_f32(part + dl_blast(n), v[0] * unscale);
+    }
+    cta_sync();
+
+    // ---- backward: stage l turns dz_l into dz_{l-1} and drains dW_l
+    for (int l = NH; l >= 1; --l) {
+      const uint32_t dz_l = aDz + (uint32_t)((NH - l) & 1) * BUF;
+      if (warp == 0) {
+        if (l >= 2) { need_w(l - 1); need_act(l - 2); }
+        need_w(l);
+        if (elect_one()) {
+          if (l >= 2) issue_forward<F>(TZ, aA + (uint32_t)(l & 1) * BUF, aWt + (uint32_t)(l & 1) * BUF);  // theta_{l-1}
+          else layer0();
+          issue_dx<F>(TXB, dz_l, aWt + (uint32_t)((l - 1) & 1) * BUF);                                     // dX_{l-1}
+          commit(&bar_mma);
+          issue_dw128<F>(TDW, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l);                                   // dW_l^T
+          commit(&bar_dw);
+        }
+        __syncwarp();
+      }
+      wait_mma();
+      if (warp == 0 && l >= 3) load_w(l - 2);  // into the buffer of W_l (dX_{l-1} is done)
+      {
+        unsigned char* dzb = sDz + (size_t)((NH - l + 1) & 1) * BUF;  // dz_{l-1}
+        const float scale = l >= 2 ? 1.0f : w0 / wh;  // dX carries w_hidden (omega-scaled weights); layer 0 wants w_0
+        for (int c = c_lo; c < c_hi; ++c) {
+          float z[16], x[16];
+          tmem_ld16(TZ + lane_base + 16 * c, z);
+          tmem_ld16(TXB + lane_base + 16 * c, x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
+          store_chunk16_both<true>(dzb, r, c, z, false, 0);
+        }
+      }
+      wait_dw();
+      if (warp == 0 && l >= 3) load_act(l - 3);  // into the buffer of a_{l-1} (dW_l is done)
+      // drain dW_l: lane r = input feature k, column = output feature o
+      {
+        float* wrow = part + dl_W(n, l) + r;
+        float* brow = part + dl_b(n, l);
+        for (int c = c_lo; c < c_hi; ++c) {  // (the TMEM load is warp-collective: only the reductions are predicated)
+          float v[16];
+          tmem_ld16(TDW + lane_base + 16 * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * c + i;
+            if (o < f) {
+              if (r < f) red_add_f32(wrow + o * F4, v[i] * unscale);
+              else if (r == f) red_add_f32(brow + o, v[i] * unscale);
+            }
+          }
+        }
+      }
+      cta_sync();
+    }
+    // ---- dW0 (+ db0): dz_0^T [x_hi, 1, x_lo, ...]; lane = output feature
+    if (warp == 0) {
+      if (elect_one()) {
+        issue_dw128<16>(TDW, aDz + (uint32_t)(NH & 1) * BUF, aX);
+        commit(&bar_dw);
+      }
+      __syncwarp();
+    }
+    wait_dw();
+    if (cg == 0) {
+      float v[16];
+      tmem_ld16(TDW + lane_base, v);
+      tmem_ld_wait();
+      if (r < f) {
+        red_add_f32(part + dl_W0(n) + 4 * r + 0, (v[0] + v[4]) * unscale);
+        red_add_f32(part + dl_W0(n) + 4 * r + 1, (v[1] + v[5]) * unscale);
+        if (n.in_dim == 3) red_add_f32(part + dl_W0(n) + 4 * r + 2, (v[2] + v[6]) * unscale);
+        red_add_f32(part + dl_b0(n) + r, v[3] * unscale);
+      }
+    }
+    cta_sync();
+  }
+
+  if (cg == 0) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);
+    if (lane == 0) s_red[q] = loss_acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (t == 0) a.loss_partials[n.slice_off + slice] = (((s_red[0] + s_red[1]) + s_red[2]) + s_red[3]) * inv_count;
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+// ==================================================================================================================
 // host side
 // ==================================================================================================================
 int tc_fpad(int f) { return ((f + 2 + 15) / 16) * 16; }  // two constant-one columns (bias hi / lo)
@@ -953,6 +1306,7 @@ size_t tc_fit_smem(int F, int L) {  // sDz[2] + ring[NS + 2] + sX[2] + sDY + ima
 
 // resident fit CTAs per SM: the launch bound (registers), shared memory (dynamic + ~8 KB static) and TMEM columns
 int tc_fit_ctas_per_sm(int F, int L) {
+  if (F > 64) return 1;  // wide kernel: the whole shared memory and all 512 TMEM columns
   const int by_bound = F >= 48 ? 1 : F == 32 ? 2 : 3;  // == FitCfg<F>::MIN_BLOCKS
   const size_t dyn = tc_fit_smem(F, L) < 49152 ? 49152 : tc_fit_smem(F, L);
   const int by_smem = (int)((size_t)227 * 1024 / (dyn + 8192));
@@ -962,9 +1316,24 @@ int tc_fit_ctas_per_sm(int F, int L) {
   return r < 1 ? 1 : r;
 }
 
+// wide fit kernel (64 < F_PAD <= 128): 2 activation + 2 dz + 2 weight buffers, X, dY, the resident tail of the image
+size_t tc_wide_smem(int F, int L) {
+  return (size_t)6 * kTile * F * 2 + 2 * (size_t)kTile * 16 * 2 + ((wide_resident_bytes(F, L - 2) + 127) & ~(size_t)127);
+}
+bool tc_wide_supported(int f, int L, int in_dim, int out_dim) {
+  const int F = tc_fpad(f);
+  if (out_dim != 1 || (in_dim != 2 && in_dim != 3)) return false;
+  if (L < 3 || F <= 64 || F > 128) return false;
+  if (tc_wide_smem(F, L) > 221 * 1024) return false;
+  return tc_eval_groups(F, L) >= 1;
+}
+// bytes of the per-CTA activation stash of the wide kernel (a_0 .. a_{NH-2}); 0 for the narrow kernel
+size_t tc_fit_stash_bytes(int F, int L) { return F > 64 && L >= 4 ? (size_t)(L - 3) * kTile * F * 2 : 0; }
+
 bool tc_supported(int f, int L, int in_dim, int out_dim) {
   const int F = tc_fpad(f);
   if (out_dim != 1 || (in_dim != 2 && in_dim != 3)) return false;
+  if (F > 64) return tc_wide_supported(f, L, in_dim, out_dim);
   if (L < 3 || F > 64) return false;
   if (3 * F + fit_acc_blocks(L - 2) * F > 512) return false;  // TMEM: Zf, Zb (x2 if it fits), Xb + packed dW accumulators
   if (tc_fit_smem(F, L) > 221 * 1024) return false;           // + ~5 KB static shared memory <= 227 KB
@@ -1016,8 +1385,23 @@ static cudaError_t launch_fit_f(const FitArgs& a, int L_max, int n_blocks, cudaS
   return cudaGetLastError();
 }
 
+template <int F>
+static cudaError_t launch_fit_wide_f(const FitArgs& a, int L_max, int n_blocks, cudaStream_t st) {
+  const size_t smem = tc_wide_smem(F, L_max);
+  if (tc_fit_stash_bytes(F, L_max) > 0 && (a.stash == nullptr || a.stash_stride < tc_fit_stash_bytes(F, L_max)))
+    return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(tc_fit_wide_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tc_fit_wide_kernel<F><<<n_blocks, kWideThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st) {
   switch (F_PAD) {
+    case 80: return launch_fit_wide_f<80>(a, L_max, n_blocks, st);
+    case 96: return launch_fit_wide_f<96>(a, L_max, n_blocks, st);
+    case 112: return launch_fit_wide_f<112>(a, L_max, n_blocks, st);
+    case 128: return launch_fit_wide_f<128>(a, L_max, n_blocks, st);
     case 16: return launch_fit_f<16>(a, L_max, n_blocks, st);
     case 32: return launch_fit_f<32>(a, L_max, n_blocks, st);
     case 48: return launch_fit_f<48>(a, L_max, n_blocks, st);
