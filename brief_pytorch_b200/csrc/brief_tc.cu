@@ -925,11 +925,13 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 //   * activations:  two [128 x F] buffers (a_j in buffer j & 1).  The forward epilogue also writes a_j (j <= NH-2) in
 //                   operand layout to a per-CTA STASH in global memory (L2-resident: 4 x 32 KB per CTA), from where
 //                   the backward pass brings it back with one bulk copy per stage;
-//   * dW:           ONE accumulator (F columns, M = 128: lane = input feature, column = output feature, so that a warp
-//                   drains 32 consecutive floats of a weight row): computed per tile and per layer, drained with
-//                   red.global.add.f32 into the slice's partial slot (fp32; one CTA per slot and a fixed tile order,
-//                   so the sum is deterministic).  That drain (~3.4 KB per sample through the L2 atomic units) is the
-//                   price of not having 768 TMEM columns.
+//   * dW:           accumulators of F columns, M = 128 (lane = input feature, column = output feature, so that a warp
+//                   touches 32 consecutive floats of a weight row).  The five hidden layers of an L = 7 network would
+//                   need 640 TMEM columns beside theta and dX, so the sums over the slice live in three places:
+//                   dW_1, dW_2 in REGISTERS (each thread adds its 64 columns of the per-tile accumulator), dW_3 in its
+//                   own TMEM accumulator, and only dW_4.. are added per tile into the slice's partial slot in L2 by a
+//                   plain read-add-write (the slot belongs to this CTA, every element to one thread; fixed tile
+//                   order, so the fp32 sums are deterministic).
 // Two threads per sample row (column halves), stages run back to back with CTA barriers: the MMA of a stage, its
 // epilogue and the drain are not overlapped with each other (only the bulk copies run ahead).  Same numerics as the
 // narrow kernel (fp16 operands, fp32 accumulation, hi/lo layer 0, kGradScale).
@@ -940,11 +942,12 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
 // D[128 x N] = A^T B over the tile's 128 samples (both operands MN-major, K = samples); rows past the operand's width
 // read whatever follows the buffer and are ignored by the drain
 template <int N>
-__device__ __forceinline__ void issue_dw128(uint32_t d, uint32_t a_buf, uint32_t b_buf) {
+__device__ __forceinline__ void issue_dw128(uint32_t d, uint32_t a_buf, uint32_t b_buf, bool accumulate = false) {
   constexpr uint32_t idesc = make_idesc(128, N, true, true);
 #pragma unroll
   for (int k = 0; k < kTile / 16; ++k)
-    mma_f16(d, make_desc(a_buf + k * 2 * 128, 128, kActLBO), make_desc(b_buf + k * 2 * 128, 128, kActLBO), idesc, k > 0);
+    mma_f16(d, make_desc(a_buf + k * 2 * 128, 128, kActLBO), make_desc(b_buf + k * 2 * 128, 128, kActLBO), idesc,
+            (accumulate || k > 0) ? 1u : 0u);
 }
 
 constexpr int kWideThreads = 256;
@@ -952,7 +955,7 @@ __host__ __device__ constexpr size_t wide_resident_bytes(int F, int NH) { return
 
 template <int F>
 __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a) {
-  constexpr int NC = F / 16;
+  constexpr int NC = F / 16, NCH = (NC + 1) / 2;  // 16-column chunks per row / per thread (two threads per row)
   constexpr uint32_t BUF = kTile * F * 2, BLK = kTile * 16 * 2;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
@@ -966,6 +969,10 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int q = warp & 3, cg = warp >> 2, r = 32 * q + lane;
   const int c_lo = cg ? (NC + 1) / 2 : 0, c_hi = cg ? NC : (NC + 1) / 2;  // this thread's 16-column chunks
+#ifdef BRIEF_TC_TIMING
+  const int tslot = warp == 0 ? 0 : -1;
+#endif
+  TT(k_start);
   const int wi = tc_find_work(a.work_prefix, a.n_work, blockIdx.x);
   const int net_id = a.work_net[wi];
   const int slice = blockIdx.x - a.work_prefix[wi];
@@ -1008,7 +1015,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   unsigned char* stash = a.stash + (size_t)blockIdx.x * a.stash_stride;  // a_j (j <= NH-2) at stash + j * BUF
 
   const uint32_t tm = tmem_base_s;
-  const uint32_t TZ = tm, TXB = tm + F, TDW = tm + 2 * F;
+  const uint32_t TZ = tm, TXB = tm + F, TDW = tm + 2 * F, TDW3 = tm + 3 * F;  // TDW3: dW_3, summed over the slice
   const uint32_t lane_base = (uint32_t)(32 * q) << 16;
   const uint32_t aA = smem_u32(sA), aDz = smem_u32(sDz), aWt = smem_u32(sWt), aX = smem_u32(sX), aDY = smem_u32(sDY),
                  aL0 = smem_u32(sRes);
@@ -1019,14 +1026,19 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
   const float unscale = 2.0f * inv_count / kGradScale;
   float loss_acc = 0.f;
+  float acc1[NCH][16], acc2[NCH][16];  // dW_1 / dW_2 (+ db) of the slice: row r, this thread's columns
+#pragma unroll
+  for (int ci = 0; ci < NCH; ++ci)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { acc1[ci][i] = 0.f; acc2[ci][i] = 0.f; }
   uint32_t ph_mma = 0, ph_dw = 0;
   // warp 0 only (kept warp-uniform): phase and "copy in flight" of the weight / activation buffers
   uint32_t ph_w[2] = {0, 0}, ph_act[2] = {0, 0};
   bool pend_w[2] = {false, false}, pend_act[2] = {false, false};
 
-  auto cta_sync = [&]() {  // operand rows written / TMEM read -> the next stage's MMAs and bulk copies may touch them
+  auto cta_sync = [&]() {  // operand rows written / TMEM read -> the next stage's MMAs may touch them
     tc_fence_before();
-    fence_async_all();
+    fence_async_smem();
     __syncthreads();
     tc_fence_after();
   };
@@ -1070,24 +1082,33 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   mbar_wait(&bar_res, 0);
   __syncthreads();
 
+  // sampler (main.py:126-163 / whole-block cube): one row per thread of the first column group, fetched one tile ahead
+  // (the index -> voxel / axis-table loads of tile k+1 are issued under the backward pass of tile k)
+  float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+  float nxt_w = 0.f;
+  auto fetch_sample = [&](int k) {
+    const long long s = s_begin + (long long)k * kTile + r;
+    const bool ok = s < s_end;
+    long long v = 0;
+    if (ok) {
+      if (n.mode == 0) v = s;
+      else if (a.idx) v = a.idx[n.idx_off + s];
+      else v = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
+    }
+    const float raw = brief_raw_value(n, v);
+    float x0, x1, x2;
+    brief_coords(n, a.axes, v, x0, x1, x2);
+    nxt = ok ? make_float4(x0, x1, x2, brief_normalize(n, raw)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    nxt_w = ok ? brief_weight(n, v, raw) : 0.f;
+  };
+  if (cg == 0 && n_tiles > 0) fetch_sample(0);
+
   for (int k = 0; k < n_tiles; ++k) {
-    // ---- sampler (main.py:126-163 / whole-block cube): one row per thread of the first column group
+    TT(t0);
     if (cg == 0) {
-      const long long s = s_begin + (long long)k * kTile + r;
-      const bool ok = s < s_end;
-      long long v = 0;
-      if (ok) {
-        if (n.mode == 0) v = s;
-        else if (a.idx) v = a.idx[n.idx_off + s];
-        else v = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
-      }
-      const float raw = brief_raw_value(n, v);
-      float x0, x1, x2;
-      brief_coords(n, a.axes, v, x0, x1, x2);
-      const float yv = ok ? brief_normalize(n, raw) : 0.f;
-      s_gw[r] = ok ? brief_weight(n, v, raw) : 0.f;
-      if (!ok) { x0 = 0.f; x1 = 0.f; x2 = 0.f; }
-      s_g[r] = make_float4(x0, x1, x2, yv);
+      const float x0 = nxt.x, x1 = nxt.y, x2 = nxt.z;
+      s_gw[r] = nxt_w;
+      s_g[r] = nxt;
       // layer-0 operand row [x_hi(3) 1 x_lo(3) 1 | x_hi(3) 0 0 0 0 0]; also the B operand of dW0
       const float h0 = __half2float(__float2half_rn(x0)), h1 = __half2float(__float2half_rn(x1)),
                   h2 = __half2float(__float2half_rn(x2));
@@ -1097,11 +1118,13 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       *reinterpret_cast<uint4*>(sX + chunk_off(r, 1, kTile)) = make_uint4(p01, pack_f16x2(h2, 0.f), 0u, 0u);
     }
     cta_sync();
+    { TT(t1); TACC(0, t1 - t0); }
     const float4 xf = s_g[r];
 
     // ---- forward: stage j computes theta_j (TZ) and a_j
     float ypart = 0.f;
     for (int j = 0; j <= NH; ++j) {
+      TT(f0);
       if (warp == 0) {
         if (j >= 1) need_w(j);
         if (elect_one()) {
@@ -1112,6 +1135,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
         __syncwarp();
       }
       wait_mma();
+      TT(f1);
       if (warp == 0 && j >= 1 && j + 2 <= NH) load_w(j + 2);  // the buffer of W_j is free again
       unsigned char* dst = sA + (size_t)(j & 1) * BUF;
       unsigned char* gst = stash + (size_t)j * BUF;
@@ -1137,10 +1161,13 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
         }
       }
       if (j == NH) s_y[cg][r] = ypart;
+      TT(f2);
       cta_sync();
+      { TT(f3); TACC(1, f1 - f0); TACC(2, f2 - f1); TACC(3, f3 - f2); }
     }
 
     // ---- loss (datal2, main.py:176-182), scaled output gradient, dz_NH (theta_NH is still in TZ)
+    TT(l0);
     const float y = s_bl[0] + s_y[0][r] + s_y[1][r];
     float dys = 0.f;
     if (s_begin + (long long)k * kTile + r < s_end) {
@@ -1159,7 +1186,10 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       for (int i = 0; i < 16; ++i) v[i] = dys * s_wl[16 * c + i] * fast_cos(v[i]);
       store_chunk16_both<true>(sDz, r, c, v, false, 0);
     }
+    fence_async_all();  // the stash rows written in the forward pass (generic proxy, global) -> the bulk copies below
     cta_sync();
+    TT(l1);
+    if (cg == 0 && k + 1 < n_tiles) fetch_sample(k + 1);
     // dWlast (+ dblast in row f): a_NH^T dY
     if (warp == 0) {
       if (elect_one()) {
@@ -1178,10 +1208,12 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       else if (r == f) red_add_f32(part + dl_blast(n), v[0] * unscale);
     }
     cta_sync();
+    { TT(l2); TACC(4, l1 - l0); TACC(5, l2 - l1); }
 
     // ---- backward: stage l turns dz_l into dz_{l-1} and drains dW_l
     for (int l = NH; l >= 1; --l) {
       const uint32_t dz_l = aDz + (uint32_t)((NH - l) & 1) * BUF;
+      TT(b0);
       if (warp == 0) {
         if (l >= 2) { need_w(l - 1); need_act(l - 2); }
         need_w(l);
@@ -1190,12 +1222,14 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
           else layer0();
           issue_dx<F>(TXB, dz_l, aWt + (uint32_t)((l - 1) & 1) * BUF);                                     // dX_{l-1}
           commit(&bar_mma);
-          issue_dw128<F>(TDW, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l);                                   // dW_l^T
+          if (l == 3) issue_dw128<F>(TDW3, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l, k > 0);               // dW_3^T, resident
+          else issue_dw128<F>(TDW, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l);                             // dW_l^T
           commit(&bar_dw);
         }
         __syncwarp();
       }
       wait_mma();
+      TT(b1);
       if (warp == 0 && l >= 3) load_w(l - 2);  // into the buffer of W_l (dX_{l-1} is done)
       {
         unsigned char* dzb = sDz + (size_t)((NH - l + 1) & 1) * BUF;  // dz_{l-1}
@@ -1210,28 +1244,54 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
           store_chunk16_both<true>(dzb, r, c, z, false, 0);
         }
       }
+      TT(b2);
       wait_dw();
+      TT(b3);
       if (warp == 0 && l >= 3) load_act(l - 3);  // into the buffer of a_{l-1} (dW_l is done)
-      // drain dW_l: lane r = input feature k, column = output feature o
-      {
-        float* wrow = part + dl_W(n, l) + r;
-        float* brow = part + dl_b(n, l);
-        for (int c = c_lo; c < c_hi; ++c) {  // (the TMEM load is warp-collective: only the reductions are predicated)
-          float v[16];
-          tmem_ld16(TDW + lane_base + 16 * c, v);
-          tmem_ld_wait();
+      // dW_l of this tile: layers 1 and 2 are summed in REGISTERS (this thread's 64 columns of its row), layer 3 stays
+      // in its own TMEM accumulator across the slice's tiles; only layers >= 4 go to the slice's partial slot per tile
+      if (l <= 2) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int o = 16 * c + i;
-            if (o < f) {
-              if (r < f) red_add_f32(wrow + o * F4, v[i] * unscale);
-              else if (r == f) red_add_f32(brow + o, v[i] * unscale);
+        for (int ci = 0; ci < NCH; ++ci) {
+          if (c_lo + ci < c_hi) {  // (warp-uniform: the TMEM load is warp-collective)
+            float v[16];
+            tmem_ld16(TDW + lane_base + 16 * (c_lo + ci), v);
+            tmem_ld_wait();
+            if (l == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc1[ci][i] += v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc2[ci][i] += v[i];
             }
           }
         }
+      } else if (l >= 4) {
+        // the slot belongs to this CTA and every element to one thread: a plain read-add-write through L2 (16 reads in
+        // flight per thread) — red.global.add ran at ~1 per clock per SM here
+        float* const wrow = part + dl_W(n, l) + r;
+        float* const brow = part + dl_b(n, l);
+        for (int c = c_lo; c < c_hi; ++c) {
+          float v[16], old[16];
+          float* dst[16];
+          tmem_ld16(TDW + lane_base + 16 * c, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int o = 16 * c + i;
+            dst[i] = (o < f && r <= f) ? (r < f ? wrow + o * F4 : brow + o) : nullptr;
+            old[i] = dst[i] ? __ldcg(dst[i]) : 0.f;
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (dst[i]) __stcg(dst[i], fmaf(v[i], unscale, old[i]));
+        }
       }
+      TT(b4);
       cta_sync();
+      { TT(b5); TACC(6, b1 - b0); TACC(7, b2 - b1); TACC(8, b3 - b2); TACC(9, b4 - b3); TACC(10, b5 - b4); }
     }
+    TT(d0);
     // ---- dW0 (+ db0): dz_0^T [x_hi, 1, x_lo, ...]; lane = output feature
     if (warp == 0) {
       if (elect_one()) {
@@ -1253,8 +1313,31 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       }
     }
     cta_sync();
+    { TT(d1); TACC(11, d1 - d0); TACC(12, 1); TACC(13, d1 - t0); }
   }
 
+  // ---- slice epilogue: the resident dW sums -> the slot (zeroed above; every element has exactly one writer)
+  if (n_tiles > 0) {
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+      if (c_lo + ci < c_hi) {
+        float v3[16];
+        if (NH >= 3) {
+          tmem_ld16(TDW3 + lane_base + 16 * (c_lo + ci), v3);
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int o = 16 * (c_lo + ci) + i;
+          if (o < f && r <= f) {
+            if (NH >= 1) __stcg(r < f ? part + dl_W(n, 1) + r + o * F4 : part + dl_b(n, 1) + o, acc1[ci][i] * unscale);
+            if (NH >= 2) __stcg(r < f ? part + dl_W(n, 2) + r + o * F4 : part + dl_b(n, 2) + o, acc2[ci][i] * unscale);
+            if (NH >= 3) __stcg(r < f ? part + dl_W(n, 3) + r + o * F4 : part + dl_b(n, 3) + o, v3[i] * unscale);
+          }
+        }
+      }
+    }
+  }
   if (cg == 0) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_down_sync(0xffffffffu, loss_acc, off);

@@ -311,9 +311,10 @@ def test_operand_image_refreshed_by_the_optimiser_equals_a_full_pack(tag, optnam
 
 @pytest.mark.parametrize("features", [70, 90, 113, 126])
 def test_wide_networks_decode_on_the_tensor_core(features):
-    """Widths above the fused fit kernel's envelope (hipct f=113): under BRIEF_PREC_AUTO the fit runs the
-    fp32 CUDA-core kernels, while forward / decompress run the tcgen05 kernel (operand image kept current by the
-    optimiser).  Per-layer pre-activations and the decoded block against the oracle, f16 tolerance."""
+    """Widths above the narrow fit kernel's envelope (hipct f=113): under BRIEF_PREC_AUTO the fit runs the
+    wide tcgen05 kernel (streamed weights, stashed activations) and forward / decompress run the tcgen05 decode kernel
+    (operand image kept current by the optimiser).  Per-layer pre-activations and the decoded block against the oracle,
+    f16 tolerance."""
     from brief_pytorch_b200 import Networks
     from brief_pytorch_b200.group import NetSpec, SirenGroup, pack_module_params
     kw = dict(coords_channel=3, data_channel=1, layers=7, w0=10, features=features)
@@ -323,7 +324,7 @@ def test_wide_networks_decode_on_the_tensor_core(features):
     torch.manual_seed(11)
     ora = O.init_phi(dict(kw, name="SIREN"))
     grp = SirenGroup([NetSpec(features, 7, 10.0, dims)], 0, "auto")
-    assert grp.precision(0) == "fp32"          # the fit path
+    assert grp.precision(0) == "f16"           # the fit path: tc_fit_wide_kernel
     grp.set_axes(0, "-1,1")
     grp.set_params(0, pack_module_params(phi))
     coords = O.create_flattened_coords(dims, "-1,1")
@@ -333,7 +334,7 @@ def test_wide_networks_decode_on_the_tensor_core(features):
     for l in range(6):
         assert relerr(zs[l].cpu().numpy(), z_ref[l].numpy()) < TOL["f16"], f"z{l}"
     assert relerr(y.cpu().numpy(), y_ref.numpy()) < TOL["f16"]
-    # a few optimiser steps (fp32 fit kernels) must leave the tensor-core image in sync with the parameters
+    # a few optimiser steps must leave the tensor-core image in sync with the parameters
     rng = np.random.default_rng(2)
     vol = rng.integers(1000, 30000, size=dims, dtype=np.uint16)[..., None]
     bind_block(grp, 0, vol, rules=[(65535, 65535, 1.0)], tau=0.0)
@@ -349,6 +350,62 @@ def test_wide_networks_decode_on_the_tensor_core(features):
     with torch.no_grad():
         y2 = O.forward_layers(O.siren_params(ora), coords, 10.0)[0].numpy().reshape(dims)
     assert relerr(a, y2) < TOL["f16"]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
+@pytest.mark.parametrize("features,layers,sampler", [(113, 7, "randompoint"), (70, 7, "randomcube"), (90, 5, "randompoint"),
+                                                     (126, 7, "randomcube"), (100, 3, "randomcube")])
+def test_wide_networks_loss_and_gradients(features, layers, sampler, prec):
+    """The wide fit kernel (64 < F_PAD <= 128) and the fp32 kernels at the same widths against the oracle's autograd on
+    the same samples: loss and every gradient tensor, several slices and a ragged last tile; then 20 optimiser steps
+    stay on the oracle's loss curve."""
+    from brief_pytorch_b200 import Networks
+    from brief_pytorch_b200.group import NetSpec, SirenGroup, pack_module_params
+    kw = dict(coords_channel=3, data_channel=1, layers=layers, w0=10, features=features)
+    dims = (6, 21, 37)   # 4662 voxels: 36 full tiles + one of 54 rows
+    torch.manual_seed(5)
+    phi = Networks.init_phi(dict(kw, name="SIREN"))
+    grp = SirenGroup([NetSpec(features, layers, 10.0, dims)], 0, prec)
+    assert grp.precision(0) == prec
+    grp.set_axes(0, "-1,1")
+    grp.set_params(0, pack_module_params(phi))
+    rng = np.random.default_rng(4)
+    vol = rng.integers(500, 30000, size=dims, dtype=np.uint16)[..., None]
+    bind_block(grp, 0, vol, rules=[(10001, 65535, 0.1)], tau=0.0)
+    n_vox = int(np.prod(dims))
+    if sampler == "randompoint":
+        idx = torch.from_numpy(rng.integers(0, n_vox, 3001)).long()
+        grp.set_sampler(0, "randompoint", 3001)
+    else:
+        idx = torch.arange(n_vox)
+        grp.set_sampler(0, "randomcube")
+    loss = grp.fit_step(idx.cuda() if sampler == "randompoint" else None)
+    # oracle: the same samples through torch autograd (fp32, CPU)
+    data_t, side = O.normalize_data(vol.copy(), "minmaxany_0_100")
+    weight = torch.from_numpy(O.parse_weight(vol, ["value_10001_65535_0.1"]))
+    coords = O.create_flattened_coords(dims, "-1,1")[idx]
+    y = data_t.reshape(-1, 1)[idx]
+    w = weight.reshape(-1, 1)[idx]
+    torch.manual_seed(5)
+    ora = O.init_phi(dict(kw, name="SIREN"))
+    ref_loss, _, ref_grads, _ = O.loss_and_grads(O.siren_params(ora), coords, y, w, 0.0, 10.0)
+    assert abs(float(loss[0]) - float(ref_loss)) < TOL[prec] * float(ref_loss)
+    grads = unpack(grp.get_grads(0), 3, features, layers)
+    for l in range(layers):
+        assert relerr(grads[l][0], ref_grads[l][0].numpy()) < 5 * TOL[prec], f"dW{l}"
+        assert relerr(grads[l][1].reshape(-1), ref_grads[l][1].numpy().reshape(-1)) < 5 * TOL[prec], f"db{l}"
+    # a short fit follows the oracle's loss curve (full-batch cube only: the same samples every step)
+    if sampler == "randomcube":
+        hist = grp.fit_run(20, "Adamax", 1e-3, seed=1, loss_history=True).cpu().numpy()[:, 0]
+        opt = torch.optim.Adamax(ora.parameters(), lr=1e-3)
+        ref_hist = []
+        for _ in range(20):
+            opt.zero_grad()
+            l_ = O.datal2(y, ora(coords), w.clone(), 0.0)
+            l_.backward()
+            opt.step()
+            ref_hist.append(float(l_))
+        assert np.abs(hist - np.array(ref_hist)).max() < 3 * TOL[prec] * ref_hist[0]
 
 
 @pytest.mark.parametrize("prec", ["fp32", "f16"])
