@@ -57,7 +57,7 @@ WORKLOADS = {
                   "randompoint batch 100000/block, Adamax; 8 blocks per GPU"),
     "hipct256": ((256, 512, 512), 128, 4, 7, 10.0, 100000,
                  "DivideTask hipct.yaml geometry (2048^3 ratio 128, Nb=512): 256^3 blocks, SIREN L=7 f=113 w0=10, "
-                 "randompoint batch 100000/block, Adamax; 4 blocks per GPU (fit on the fp32 CUDA-core kernels, decode on tcgen05)"),
+                 "randompoint batch 100000/block, Adamax; 4 blocks per GPU (wide tcgen05 fit kernel: streamed weights, stashed activations)"),
 }
 
 

@@ -928,10 +928,11 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 //   * dW:           accumulators of F columns, M = 128 (lane = input feature, column = output feature, so that a warp
 //                   touches 32 consecutive floats of a weight row).  The five hidden layers of an L = 7 network would
 //                   need 640 TMEM columns beside theta and dX, so the sums over the slice live in three places:
-//                   dW_1, dW_2 in REGISTERS (each thread adds its 64 columns of the per-tile accumulator), dW_3 in its
-//                   own TMEM accumulator, and only dW_4.. are added per tile into the slice's partial slot in L2 by a
-//                   plain read-add-write (the slot belongs to this CTA, every element to one thread; fixed tile
-//                   order, so the fp32 sums are deterministic).
+//                   dW_1 in REGISTERS (each thread adds its 64 columns of the per-tile accumulator), dW_3 in its own
+//                   TMEM accumulator, and the others are added per tile into a per-CTA scratch in L2 by a plain
+//                   16-byte read-add-write whose reads are issued a whole stage early; the scratch is laid out so that
+//                   a warp's access is 512 contiguous bytes (every element belongs to one thread; fixed tile order, so
+//                   the fp32 sums are deterministic).  The slice's partial slot is written once, at the end.
 // Two threads per sample row (column halves), stages run back to back with CTA barriers: the MMA of a stage, its
 // epilogue and the drain are not overlapped with each other (only the bulk copies run ahead).  Same numerics as the
 // narrow kernel (fp16 operands, fp32 accumulation, hi/lo layer 0, kGradScale).
@@ -1013,6 +1014,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   float* part = a.partials + n.part_off + (long long)slice * n.P_dev;
   for (int i = t; i < (n.P_dev >> 2); i += kWideThreads) reinterpret_cast<float4*>(part)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   unsigned char* stash = a.stash + (size_t)blockIdx.x * a.stash_stride;  // a_j (j <= NH-2) at stash + j * BUF
+  float4* scr = reinterpret_cast<float4*>(stash + (size_t)(NH >= 2 ? NH - 1 : 0) * BUF);  // running dW sums, see below
 
   const uint32_t tm = tmem_base_s;
   const uint32_t TZ = tm, TXB = tm + F, TDW = tm + 2 * F, TDW3 = tm + 3 * F;  // TDW3: dW_3, summed over the slice
@@ -1026,11 +1028,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
   const float unscale = 2.0f * inv_count / kGradScale;
   float loss_acc = 0.f;
-  float acc1[NCH][16], acc2[NCH][16];  // dW_1 / dW_2 (+ db) of the slice: row r, this thread's columns
+  float acc1[NCH][16];  // dW_1^T (+ db_1) of the slice: row r = input feature, this thread's output-feature columns
 #pragma unroll
   for (int ci = 0; ci < NCH; ++ci)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { acc1[ci][i] = 0.f; acc2[ci][i] = 0.f; }
+    for (int i = 0; i < 16; ++i) acc1[ci][i] = 0.f;
   uint32_t ph_mma = 0, ph_dw = 0;
   // warp 0 only (kept warp-uniform): phase and "copy in flight" of the weight / activation buffers
   uint32_t ph_w[2] = {0, 0}, ph_act[2] = {0, 0};
@@ -1214,6 +1216,18 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
     for (int l = NH; l >= 1; --l) {
       const uint32_t dz_l = aDz + (uint32_t)((NH - l) & 1) * BUF;
       TT(b0);
+      // layers summed in the CTA's scratch (all but 1 and 3): this thread's 16 float4 of the running sum are read NOW,
+      // so that the L2 latency sits under the MMAs and the cosine epilogue of this stage.  Scratch layout
+      // [chunk][float4 i][row r]: a warp's access is 512 contiguous bytes (weight rows in the slot have a 464-byte
+      // pitch: the same float4 access there touches 32 lines per instruction and ran 8x slower).
+      const bool drained = l == 2 || l >= 4;
+      float4* const scr_l = scr + (size_t)(l == 2 ? 0 : l - 3) * (NC * 4 * kTile) + r;  // + (16-col chunk * 4 + i) * 128
+      float4 pf[NCH][4];
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pf[ci][i] = (drained && k > 0 && c_lo + ci < c_hi) ? scr_l[((c_lo + ci) * 4 + i) * kTile] : make_float4(0.f, 0.f, 0.f, 0.f);
       if (warp == 0) {
         if (l >= 2) { need_w(l - 1); need_act(l - 2); }
         need_w(l);
@@ -1222,8 +1236,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
           else layer0();
           issue_dx<F>(TXB, dz_l, aWt + (uint32_t)((l - 1) & 1) * BUF);                                     // dX_{l-1}
           commit(&bar_mma);
-          if (l == 3) issue_dw128<F>(TDW3, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l, k > 0);               // dW_3^T, resident
-          else issue_dw128<F>(TDW, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l);                             // dW_l^T
+          if (l == 3) issue_dw128<F>(TDW3, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l, k > 0);  // dW_3^T, resident
+          else if (l == 1) issue_dw128<F>(TDW, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l);      // dW_1^T [in][out]
+          else issue_dw128<F>(TDW, dz_l, aA + (uint32_t)((l - 1) & 1) * BUF);                  // dW_l [out][in]
           commit(&bar_dw);
         }
         __syncwarp();
@@ -1248,43 +1263,33 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       wait_dw();
       TT(b3);
       if (warp == 0 && l >= 3) load_act(l - 3);  // into the buffer of a_{l-1} (dW_l is done)
-      // dW_l of this tile: layers 1 and 2 are summed in REGISTERS (this thread's 64 columns of its row), layer 3 stays
-      // in its own TMEM accumulator across the slice's tiles; only layers >= 4 go to the slice's partial slot per tile
-      if (l <= 2) {
+      // dW_l of this tile: layer 1 is summed in REGISTERS (this thread's 64 columns of its row), layer 3 stays in its
+      // own TMEM accumulator across the slice's tiles, the others are added into the CTA's scratch in L2: every element
+      // belongs to one thread, so a plain 16-byte read (above) - add - write replaces atomics (red.global.add ran at
+      // ~1 per clock per SM here)
+      if (l == 1) {
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           if (c_lo + ci < c_hi) {  // (warp-uniform: the TMEM load is warp-collective)
             float v[16];
             tmem_ld16(TDW + lane_base + 16 * (c_lo + ci), v);
             tmem_ld_wait();
-            if (l == 1) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) acc1[ci][i] += v[i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) acc2[ci][i] += v[i];
-            }
+            for (int i = 0; i < 16; ++i) acc1[ci][i] += v[i];
           }
         }
-      } else if (l >= 4) {
-        // the slot belongs to this CTA and every element to one thread: a plain read-add-write through L2 (16 reads in
-        // flight per thread) — red.global.add ran at ~1 per clock per SM here
-        float* const wrow = part + dl_W(n, l) + r;
-        float* const brow = part + dl_b(n, l);
-        for (int c = c_lo; c < c_hi; ++c) {
-          float v[16], old[16];
-          float* dst[16];
-          tmem_ld16(TDW + lane_base + 16 * c, v);
+      } else if (drained) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int o = 16 * c + i;
-            dst[i] = (o < f && r <= f) ? (r < f ? wrow + o * F4 : brow + o) : nullptr;
-            old[i] = dst[i] ? __ldcg(dst[i]) : 0.f;
+        for (int ci = 0; ci < NCH; ++ci) {
+          if (c_lo + ci < c_hi) {
+            float v[16];
+            tmem_ld16(TDW + lane_base + 16 * (c_lo + ci), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              scr_l[((c_lo + ci) * 4 + i) * kTile] = make_float4(pf[ci][i].x + v[4 * i], pf[ci][i].y + v[4 * i + 1],
+                                                                 pf[ci][i].z + v[4 * i + 2], pf[ci][i].w + v[4 * i + 3]);
           }
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (dst[i]) __stcg(dst[i], fmaf(v[i], unscale, old[i]));
         }
       }
       TT(b4);
@@ -1316,8 +1321,28 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
     { TT(d1); TACC(11, d1 - d0); TACC(12, 1); TACC(13, d1 - t0); }
   }
 
-  // ---- slice epilogue: the resident dW sums -> the slot (zeroed above; every element has exactly one writer)
+  // ---- slice epilogue: the dW sums -> the slot (zeroed above; every element has exactly one writer)
   if (n_tiles > 0) {
+    for (int l = 2; l <= NH; ++l) {  // scratch layers: lane r = output feature, chunks of 16 input features
+      if (l == 3) continue;
+      const float4* scr_l = scr + (size_t)(l == 2 ? 0 : l - 3) * (NC * 4 * kTile) + r;
+      float* const wrow = part + dl_W(n, l) + r * F4;
+      if (r < f) {
+        for (int c = c_lo; c < c_hi; ++c)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k0 = 16 * c + 4 * i;
+            if (k0 > f) continue;
+            const float4 v = scr_l[(c * 4 + i) * kTile];
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (k0 + j < f) wrow[k0 + j] = e[j] * unscale;
+              else if (k0 + j == f) part[dl_b(n, l) + r] = e[j] * unscale;
+            }
+          }
+      }
+    }
 #pragma unroll
     for (int ci = 0; ci < NCH; ++ci) {
       if (c_lo + ci < c_hi) {
@@ -1331,7 +1356,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
           const int o = 16 * (c_lo + ci) + i;
           if (o < f && r <= f) {
             if (NH >= 1) __stcg(r < f ? part + dl_W(n, 1) + r + o * F4 : part + dl_b(n, 1) + o, acc1[ci][i] * unscale);
-            if (NH >= 2) __stcg(r < f ? part + dl_W(n, 2) + r + o * F4 : part + dl_b(n, 2) + o, acc2[ci][i] * unscale);
             if (NH >= 3) __stcg(r < f ? part + dl_W(n, 3) + r + o * F4 : part + dl_b(n, 3) + o, v3[i] * unscale);
           }
         }
@@ -1410,8 +1434,14 @@ bool tc_wide_supported(int f, int L, int in_dim, int out_dim) {
   if (tc_wide_smem(F, L) > 221 * 1024) return false;
   return tc_eval_groups(F, L) >= 1;
 }
-// bytes of the per-CTA activation stash of the wide kernel (a_0 .. a_{NH-2}); 0 for the narrow kernel
-size_t tc_fit_stash_bytes(int F, int L) { return F > 64 && L >= 4 ? (size_t)(L - 3) * kTile * F * 2 : 0; }
+// bytes of the wide kernel's per-CTA scratch: the activation stash (a_0 .. a_{NH-2}) followed by the running dW sums of
+// the layers that are kept neither in registers (1) nor in TMEM (3); 0 for the narrow kernel
+size_t tc_fit_stash_bytes(int F, int L) {
+  if (F <= 64) return 0;
+  const int NH = L - 2;
+  const int scratch_layers = NH - (NH >= 1 ? 1 : 0) - (NH >= 3 ? 1 : 0);
+  return (size_t)(NH >= 2 ? NH - 1 : 0) * kTile * F * 2 + (size_t)scratch_layers * (F / 16) * 4 * kTile * 16;
+}
 
 bool tc_supported(int f, int L, int in_dim, int out_dim) {
   const int F = tc_fpad(f);

@@ -404,7 +404,7 @@ def test_wide_networks_loss_and_gradients(features, layers, sampler, prec):
             l_ = O.datal2(y, ora(coords), w.clone(), 0.0)
             l_.backward()
             opt.step()
-            ref_hist.append(float(l_))
+            ref_hist.append(float(l_.detach()))
         assert np.abs(hist - np.array(ref_hist)).max() < 3 * TOL[prec] * ref_hist[0]
 
 

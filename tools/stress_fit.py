@@ -13,7 +13,7 @@ worst = 0.0
 for case in range(n_cases):
     L = int(rng.choice([3, 4, 5, 7, 8]))
     nets = int(rng.integers(1, 6))
-    fs = [int(rng.choice([3, 5, 13, 14, 22, 30, 31, 39, 46, 47, 56, 62])) for _ in range(nets)]
+    fs = [int(rng.choice([3, 5, 13, 14, 22, 30, 31, 39, 46, 47, 56, 62, 63, 70, 78, 94, 113, 126])) for _ in range(nets)]
     dims = [tuple(int(x) for x in rng.integers(3, 40, size=3)) for _ in range(nets)]
     modes = [str(rng.choice(["randomcube", "randompoint"])) for _ in range(nets)]
     batches = [int(rng.integers(1, 5000)) for _ in range(nets)]
