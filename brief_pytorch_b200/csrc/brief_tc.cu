@@ -928,8 +928,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
 //   * dW:           accumulators of F columns, M = 128 (lane = input feature, column = output feature, so that a warp
 //                   touches 32 consecutive floats of a weight row).  The five hidden layers of an L = 7 network would
 //                   need 640 TMEM columns beside theta and dX, so the sums over the slice live in three places:
-//                   dW_1 in REGISTERS (each thread adds its 64 columns of the per-tile accumulator), dW_3 in its own
-//                   TMEM accumulator, and the others are added per tile into a per-CTA scratch in L2 by a plain
+//                   dW_3 in its own TMEM accumulator (lane = input feature), and the others (lane = output feature) are
+//                   added per tile into a per-CTA scratch in L2 by a plain
 //                   16-byte read-add-write whose reads are issued a whole stage early; the scratch is laid out so that
 //                   a warp's access is 512 contiguous bytes (every element belongs to one thread; fixed tile order, so
 //                   the fp32 sums are deterministic).  The slice's partial slot is written once, at the end.
@@ -1028,11 +1028,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   const float inv_count = 1.0f / ((float)n.batch * (float)n.out_dim);
   const float unscale = 2.0f * inv_count / kGradScale;
   float loss_acc = 0.f;
-  float acc1[NCH][16];  // dW_1^T (+ db_1) of the slice: row r = input feature, this thread's output-feature columns
-#pragma unroll
-  for (int ci = 0; ci < NCH; ++ci)
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc1[ci][i] = 0.f;
   uint32_t ph_mma = 0, ph_dw = 0;
   // warp 0 only (kept warp-uniform): phase and "copy in flight" of the weight / activation buffers
   uint32_t ph_w[2] = {0, 0}, ph_act[2] = {0, 0};
@@ -1142,10 +1137,15 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       unsigned char* dst = sA + (size_t)(j & 1) * BUF;
       unsigned char* gst = stash + (size_t)j * BUF;
       const bool to_stash = j <= NH - 2;
-      for (int c = c_lo; c < c_hi; ++c) {
-        float v[16];
-        tmem_ld16(TZ + lane_base + 16 * c, v);
+      float vb[2][16];
+      tmem_ld16(TZ + lane_base + 16 * c_lo, vb[0]);
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int c = c_lo + ci;
+        if (c >= c_hi) break;
         tmem_ld_wait();
+        if (c + 1 < c_hi) tmem_ld16(TZ + lane_base + 16 * (c + 1), vb[(ci + 1) & 1]);  // under this chunk's sines
+        float* v = vb[ci & 1];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = fast_sin(v[i]);
         const uint4 lo4 = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
@@ -1162,13 +1162,16 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
           for (int i = 0; i < 16; ++i) ypart = fmaf(s_wl[16 * c + i], v[i], ypart);
         }
       }
-      if (j == NH) s_y[cg][r] = ypart;
+      if (j == NH) {
+        s_y[cg][r] = ypart;
+        fence_async_all();  // the stash rows written above (generic proxy, global) -> the backward pass's bulk copies
+      }
       TT(f2);
       cta_sync();
       { TT(f3); TACC(1, f1 - f0); TACC(2, f2 - f1); TACC(3, f3 - f2); }
     }
 
-    // ---- loss (datal2, main.py:176-182), scaled output gradient, dz_NH (theta_NH is still in TZ)
+    // ---- loss (datal2, main.py:176-182), scaled output gradient, dWlast, dz_NH (theta_NH is still in TZ)
     TT(l0);
     const float y = s_bl[0] + s_y[0][r] + s_y[1][r];
     float dys = 0.f;
@@ -1179,6 +1182,20 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       dys = kGradScale * wt * e;
     }
     if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
+    cta_sync();
+    TT(l1);
+    // dWlast (+ dblast in row f) = a_NH^T dY first: as soon as it has consumed a_NH, the bulk copy of a_{NH-2} into that
+    // buffer starts and runs under the dz_NH pass below
+    if (warp == 0) {
+      if (elect_one()) {
+        issue_dw128<16>(TDW, aA + (uint32_t)(NH & 1) * BUF, aDY);
+        commit(&bar_dw);
+      }
+      __syncwarp();
+    }
+    if (cg == 0 && k + 1 < n_tiles) fetch_sample(k + 1);
+    wait_dw();
+    if (warp == 0 && NH >= 2) load_act(NH - 2);
     dys *= wh;
     for (int c = c_lo; c < c_hi; ++c) {
       float v[16];
@@ -1188,20 +1205,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       for (int i = 0; i < 16; ++i) v[i] = dys * s_wl[16 * c + i] * fast_cos(v[i]);
       store_chunk16_both<true>(sDz, r, c, v, false, 0);
     }
-    fence_async_all();  // the stash rows written in the forward pass (generic proxy, global) -> the bulk copies below
-    cta_sync();
-    TT(l1);
-    if (cg == 0 && k + 1 < n_tiles) fetch_sample(k + 1);
-    // dWlast (+ dblast in row f): a_NH^T dY
-    if (warp == 0) {
-      if (elect_one()) {
-        issue_dw128<16>(TDW, aA + (uint32_t)(NH & 1) * BUF, aDY);
-        commit(&bar_dw);
-      }
-      __syncwarp();
-    }
-    wait_dw();
-    if (warp == 0 && NH >= 2) load_act(NH - 2);  // into the buffer of a_NH, which dWlast has consumed
     if (cg == 0) {
       float v[16];
       tmem_ld16(TDW + lane_base, v);
@@ -1216,12 +1219,12 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
     for (int l = NH; l >= 1; --l) {
       const uint32_t dz_l = aDz + (uint32_t)((NH - l) & 1) * BUF;
       TT(b0);
-      // layers summed in the CTA's scratch (all but 1 and 3): this thread's 16 float4 of the running sum are read NOW,
+      // layers summed in the CTA's scratch (all but 3): this thread's 16 float4 of the running sum are read NOW,
       // so that the L2 latency sits under the MMAs and the cosine epilogue of this stage.  Scratch layout
       // [chunk][float4 i][row r]: a warp's access is 512 contiguous bytes (weight rows in the slot have a 464-byte
       // pitch: the same float4 access there touches 32 lines per instruction and ran 8x slower).
-      const bool drained = l == 2 || l >= 4;
-      float4* const scr_l = scr + (size_t)(l == 2 ? 0 : l - 3) * (NC * 4 * kTile) + r;  // + (16-col chunk * 4 + i) * 128
+      const bool drained = l != 3;
+      float4* const scr_l = scr + (size_t)(l < 3 ? l - 1 : l - 2) * (NC * 4 * kTile) + r;  // + (16-col chunk * 4 + i) * 128
       float4 pf[NCH][4];
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci)
@@ -1237,7 +1240,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
           issue_dx<F>(TXB, dz_l, aWt + (uint32_t)((l - 1) & 1) * BUF);                                     // dX_{l-1}
           commit(&bar_mma);
           if (l == 3) issue_dw128<F>(TDW3, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l, k > 0);  // dW_3^T, resident
-          else if (l == 1) issue_dw128<F>(TDW, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l);      // dW_1^T [in][out]
           else issue_dw128<F>(TDW, dz_l, aA + (uint32_t)((l - 1) & 1) * BUF);                  // dW_l [out][in]
           commit(&bar_dw);
         }
@@ -1249,11 +1251,20 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       {
         unsigned char* dzb = sDz + (size_t)((NH - l + 1) & 1) * BUF;  // dz_{l-1}
         const float scale = l >= 2 ? 1.0f : w0 / wh;  // dX carries w_hidden (omega-scaled weights); layer 0 wants w_0
-        for (int c = c_lo; c < c_hi; ++c) {
-          float z[16], x[16];
-          tmem_ld16(TZ + lane_base + 16 * c, z);
-          tmem_ld16(TXB + lane_base + 16 * c, x);
+        float zb[2][16], xb[2][16];
+        tmem_ld16(TZ + lane_base + 16 * c_lo, zb[0]);
+        tmem_ld16(TXB + lane_base + 16 * c_lo, xb[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = c_lo + ci;
+          if (c >= c_hi) break;
           tmem_ld_wait();
+          if (c + 1 < c_hi) {
+            tmem_ld16(TZ + lane_base + 16 * (c + 1), zb[(ci + 1) & 1]);
+            tmem_ld16(TXB + lane_base + 16 * (c + 1), xb[(ci + 1) & 1]);
+          }
+          float* z = zb[ci & 1];
+          const float* x = xb[ci & 1];
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
           store_chunk16_both<true>(dzb, r, c, z, false, 0);
@@ -1263,22 +1274,10 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       wait_dw();
       TT(b3);
       if (warp == 0 && l >= 3) load_act(l - 3);  // into the buffer of a_{l-1} (dW_l is done)
-      // dW_l of this tile: layer 1 is summed in REGISTERS (this thread's 64 columns of its row), layer 3 stays in its
-      // own TMEM accumulator across the slice's tiles, the others are added into the CTA's scratch in L2: every element
-      // belongs to one thread, so a plain 16-byte read (above) - add - write replaces atomics (red.global.add ran at
-      // ~1 per clock per SM here)
-      if (l == 1) {
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          if (c_lo + ci < c_hi) {  // (warp-uniform: the TMEM load is warp-collective)
-            float v[16];
-            tmem_ld16(TDW + lane_base + 16 * (c_lo + ci), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc1[ci][i] += v[i];
-          }
-        }
-      } else if (drained) {
+      // dW_l of this tile: layer 3 stays in its own TMEM accumulator across the slice's tiles, the others are added into
+      // the CTA's scratch in L2: every element belongs to one thread, so a plain 16-byte read (above) - add - write
+      // replaces atomics (red.global.add ran at ~1 per clock per SM here)
+      if (drained) {
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           if (c_lo + ci < c_hi) {
@@ -1323,9 +1322,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
 
   // ---- slice epilogue: the dW sums -> the slot (zeroed above; every element has exactly one writer)
   if (n_tiles > 0) {
-    for (int l = 2; l <= NH; ++l) {  // scratch layers: lane r = output feature, chunks of 16 input features
+    for (int l = 1; l <= NH; ++l) {  // scratch layers: lane r = output feature, chunks of 16 input features
       if (l == 3) continue;
-      const float4* scr_l = scr + (size_t)(l == 2 ? 0 : l - 3) * (NC * 4 * kTile) + r;
+      const float4* scr_l = scr + (size_t)(l < 3 ? l - 1 : l - 2) * (NC * 4 * kTile) + r;
       float* const wrow = part + dl_W(n, l) + r * F4;
       if (r < f) {
         for (int c = c_lo; c < c_hi; ++c)
@@ -1355,7 +1354,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
         for (int i = 0; i < 16; ++i) {
           const int o = 16 * (c_lo + ci) + i;
           if (o < f && r <= f) {
-            if (NH >= 1) __stcg(r < f ? part + dl_W(n, 1) + r + o * F4 : part + dl_b(n, 1) + o, acc1[ci][i] * unscale);
             if (NH >= 3) __stcg(r < f ? part + dl_W(n, 3) + r + o * F4 : part + dl_b(n, 3) + o, v3[i] * unscale);
           }
         }
@@ -1435,11 +1433,11 @@ bool tc_wide_supported(int f, int L, int in_dim, int out_dim) {
   return tc_eval_groups(F, L) >= 1;
 }
 // bytes of the wide kernel's per-CTA scratch: the activation stash (a_0 .. a_{NH-2}) followed by the running dW sums of
-// the layers that are kept neither in registers (1) nor in TMEM (3); 0 for the narrow kernel
+// the layers that are not kept in TMEM (all but 3); 0 for the narrow kernel
 size_t tc_fit_stash_bytes(int F, int L) {
   if (F <= 64) return 0;
   const int NH = L - 2;
-  const int scratch_layers = NH - (NH >= 1 ? 1 : 0) - (NH >= 3 ? 1 : 0);
+  const int scratch_layers = NH - (NH >= 3 ? 1 : 0);
   return (size_t)(NH >= 2 ? NH - 1 : 0) * kTile * F * 2 + (size_t)scratch_layers * (F / 16) * 4 * kTile * 16;
 }
 

@@ -19,3 +19,8 @@ echo "ncu fit rc=$?"
 $SHORT > $out/plain_$tag.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:tc_eval_kernel -s 1 -c 1 -f -o $out/prof_eval_$tag $SHORT > $out/ncu_eval_$tag.log 2>&1
 echo "ncu eval rc=$?"
+WIDE="python bench.py --workload hipct256 --steps 3 --warmup 3 --no-cpu-baseline"
+$WIDE > $out/plain_wide_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:tc_fit_wide_kernel -s 4 -c 1 -f -o $out/prof_fit_wide_$tag $WIDE > $out/ncu_fit_wide_$tag.log 2>&1
+echo "ncu wide fit rc=$?"
+python bench.py --workload hipct256 > $out/bench_hipct256_$tag.json 2>> $out/bench_$tag.err; echo "hipct bench rc=$?"; cat $out/bench_hipct256_$tag.json
