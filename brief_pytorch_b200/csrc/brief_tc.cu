@@ -1229,20 +1229,13 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
         if (l >= 2) { need_w(l - 1); need_act(l - 2); }
         need_w(l);
         if (elect_one()) {
-#ifdef BRIEF_WIDE_DW_FIRST
-          if (l == 3) issue_dw128<F>(TDW3, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l, k > 0);  // dW_3^T, resident
-          else issue_dw128<F>(TDW, dz_l, aA + (uint32_t)((l - 1) & 1) * BUF);                  // dW_l [out][in]
-          commit(&bar_dw);
-#endif
           if (l >= 2) issue_forward<F>(TZ, aA + (uint32_t)(l & 1) * BUF, aWt + (uint32_t)(l & 1) * BUF);  // theta_{l-1}
           else layer0();
           issue_dx<F>(TXB, dz_l, aWt + (uint32_t)((l - 1) & 1) * BUF);                                     // dX_{l-1}
           commit(&bar_mma);
-#ifndef BRIEF_WIDE_DW_FIRST
           if (l == 3) issue_dw128<F>(TDW3, aA + (uint32_t)((l - 1) & 1) * BUF, dz_l, k > 0);  // dW_3^T, resident
           else issue_dw128<F>(TDW, dz_l, aA + (uint32_t)((l - 1) & 1) * BUF);                  // dW_l [out][in]
           commit(&bar_dw);
-#endif
         }
         __syncwarp();
       }
@@ -1252,10 +1245,6 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           pf[ci][i] = (drained && k > 0 && c_lo + ci < c_hi) ? scr_l[((c_lo + ci) * 4 + i) * kTile] : make_float4(0.f, 0.f, 0.f, 0.f);
-#ifdef BRIEF_WIDE_DW_FIRST
-      wait_dw();
-      if (warp == 0 && l >= 3) load_act(l - 3);  // into the buffer of a_{l-1} (dW_l is done)
-#endif
       wait_mma();
       TT(b1);
       if (warp == 0 && l >= 3) load_w(l - 2);  // into the buffer of W_l (dX_{l-1} is done)
@@ -1282,13 +1271,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
         }
       }
       TT(b2);
-#ifndef BRIEF_WIDE_DW_FIRST
       wait_dw();
-#endif
       TT(b3);
-#ifndef BRIEF_WIDE_DW_FIRST
       if (warp == 0 && l >= 3) load_act(l - 3);  // into the buffer of a_{l-1} (dW_l is done)
-#endif
       // dW_l of this tile: layer 3 stays in its own TMEM accumulator across the slice's tiles, the others are added into
       // the CTA's scratch in L2: every element belongs to one thread, so a plain 16-byte read (above) - add - write
       // replaces atomics (red.global.add ran at ~1 per clock per SM here)

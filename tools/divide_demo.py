@@ -44,6 +44,9 @@ ap.add_argument("--steps", type=int, default=300)
 ap.add_argument("--shape", default="32,128,128")
 ap.add_argument("--ratio", type=float, default=32)
 ap.add_argument("--out", default="/tmp/brief_demo")
+ap.add_argument("--data", default="vessel", choices=["vessel", "hipct", "neuron"])
+ap.add_argument("--alloc", default="by_size", choices=["by_size", "by_var"])
+ap.add_argument("--sampler", default="randomcube")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -51,8 +54,10 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 OPT["Compress"]["divide"]["divide_type"] = f"adaptotal_-1_-1_-1_{args.nb}"
 OPT["Compress"]["param"]["filesize_ratio"] = args.ratio
+OPT["Compress"]["divide"]["param_alloc"] = args.alloc
+OPT["Compress"]["sampler"]["name"] = args.sampler
 shape = tuple(int(x) for x in args.shape.split(","))
-vol = synth.vessel(shape, seed=42)
+vol = getattr(synth, args.data)(shape, seed=42)
 cdir = os.path.join(args.out, "compressed")
 if rank == 0:
     shutil.rmtree(args.out, ignore_errors=True)
@@ -76,10 +81,10 @@ if rank == 0:
     t0 = time.perf_counter()
     dec = cf.decompress_divide(os.path.join(cdir, "sideinfos.yaml"), os.path.join(cdir, "module"), os.path.join(cdir, "sideinfos"))
     t_dec = time.perf_counter() - t0
-    perf = misc.eval_performance(args.steps, vol, dec)  # utils/misc.py:477-499: float32 copies, range = dtype max
+    perf = misc.eval_performance(args.steps, vol, dec, device="cuda")  # utils/misc.py:477-499 on the device (brief_volume_quality)
     files = sum(len(f) for _, _, f in os.walk(cdir))
     nbytes = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(os.path.join(cdir, "module")) for f in fs)
-    print(json.dumps({"world": world, "shape": shape, "blocks": len(blocks), "features": blocks[0].features, "steps": args.steps,
+    print(json.dumps({"world": world, "shape": shape, "blocks": len(blocks), "features": sorted({b.features for b in blocks}), "data": args.data, "alloc": args.alloc, "steps": args.steps,
                       "fit_s": round(t_fit, 3), "decode_s": round(t_dec, 3), "module_bytes": nbytes, "files": files,
                       "ratio_actual": round(vol.nbytes / nbytes, 2),
                       "psnr_db": round(float(perf["psnr"]), 3), "ssim": round(float(perf["ssim"]), 5),
