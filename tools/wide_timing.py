@@ -20,14 +20,14 @@ grp.fit_run(3)
 torch.cuda.synchronize()
 l = _cabi.load()
 buf = (ctypes.c_ulonglong * 64)()
-l.brief_debug_read_timing.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
-l.brief_debug_read_timing(buf, 1)
+l.brief_debug_read_timing_wide.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
+l.brief_debug_read_timing_wide(buf, 1)
 n_runs = 10
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); grp.fit_run(n_runs); e1.record()
 torch.cuda.synchronize()
 print(f"f={f} L={L} nets={nets}: {e0.elapsed_time(e1) / n_runs * 1e3:.1f} us per step (instrumented build)")
-l.brief_debug_read_timing(buf, 0)
+l.brief_debug_read_timing_wide(buf, 0)
 v = list(buf)
 tiles = max(1, v[12])
 names = ["sampler + sync", f"fwd: issue + MMA wait x{L - 1}", f"fwd: sine epilogue x{L - 1}", f"fwd: sync x{L - 1}", "loss + dz_NH + sync",
