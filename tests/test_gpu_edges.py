@@ -130,6 +130,15 @@ def test_zero_length_and_error_paths():
     assert e.value.code == -3
     with pytest.raises(_cabi.BriefError):           # zero networks
         SirenGroup([], 0, "auto")
+    # envelope of the tensor-core fit kernels under "auto": fused kernel up to f = 62, wide kernel up to f = 126
+    # (F_PAD = f + 2 rounded up to 16 <= 128), fp32 CUDA-core kernels beyond; the decode kernel follows the same F_PAD
+    for f, want in ((62, "f16"), (63, "f16"), (126, "f16"), (127, "fp32"), (228, "fp32")):
+        g = SirenGroup([NetSpec(f, 7, 10.0, (4, 4, 4))], 0, "auto")
+        assert g.precision(0) == want, (f, g.precision(0))
+        g.close()
+    with pytest.raises(_cabi.BriefError) as e:      # f = 127 has no tensor-core fit kernel
+        SirenGroup([NetSpec(127, 7, 10.0, (4, 4, 4))], 0, "f16")
+    assert e.value.code == -3
 
 
 @pytest.mark.parametrize("prec", ["fp32", "f16"])

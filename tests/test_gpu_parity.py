@@ -435,6 +435,33 @@ def test_config1_3000_steps_quality_tracks_the_reference(prec):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "f16"])
+def test_wide_network_600_steps_track_the_reference(prec):
+    """A wide network (L = 5, f = 70: F_PAD = 80, the wide tcgen05 fit kernel's first bucket) fitted for 600 full-batch
+    Adamax steps on the shipped block against the UNMODIFIED reference on the CPU (oracle/gen_golden_wide.py): the loss
+    curve at every step of the first 100 and every 50th after, and the decoded PSNR / SSIM at the end."""
+    g, vol = load_gold("wide70_600"), load_gold("brain64")["volume"]
+    f, steps = int(g["features"]), int(g["steps"])
+    kw = dict(coords_channel=3, layers=5, w0=20, features=f)
+    grp = make_group([spec_of(kw, (64, 64, 64))], prec)
+    assert grp.precision(0) == prec
+    grp.set_axes(0, "-1,1")
+    grp.set_params(0, g["p0"])
+    bind_block(grp, 0, vol, rules=[(65535, 65535, 1.0)], tau=float(g["thr"]))
+    grp.set_sampler(0, "randomcube")
+    hist = grp.fit_run(steps, "Adamax", 1e-3, milestones=(50000, 60000, 70000), gamma=0.2, loss_history=True)
+    losses = hist[:, 0].cpu().numpy()
+    ref = g["losses"]
+    np.testing.assert_allclose(losses[:100], ref[:100], rtol=3 * TOL[prec])
+    np.testing.assert_allclose(losses[49::50], ref[49::50], rtol=5e-2)   # a fast-descending fit drifts through rounding alone
+    dec = u16(grp.decompress("uint16")[0])[..., None]
+    a = vol.astype(np.float32)
+    psnr, ssim = O.cal_psnr(a, dec.astype(np.float32), 65535), O.cal_ssim(a, dec.astype(np.float32), 65535)
+    print(f"[{prec}] psnr {psnr:.4f} (reference {float(g['psnr']):.4f})  ssim {ssim:.5f} (reference {float(g['ssim']):.5f})")
+    assert abs(psnr - float(g["psnr"])) < 0.25
+    assert abs(ssim - float(g["ssim"])) < 0.004
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
 def test_config1_full_budget_quality_within_north_star_bars(prec):
     """SingleTask default.yaml's full step budget (20000 full-batch Adamax steps on the shipped block), golden from the
     unmodified reference on the CPU (oracle/gen_golden_long.py 20000): decoded PSNR within 0.1 dB and SSIM within 0.002
