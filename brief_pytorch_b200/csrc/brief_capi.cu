@@ -61,6 +61,7 @@ int tc_eval_tpb(long long total_tiles, int num_sms) {
   return (int)std::min<long long>(128, std::max<long long>(8, t));
 }
 constexpr int kBuckets = 9;  // F_PAD / 16 in 1..8
+constexpr int kWideStashSlots = 256;  // SM ids (%smid) the wide fit kernel's per-SM scratch covers; the kernel traps beyond
 
 template <class T>
 struct DevBuf {
@@ -317,12 +318,12 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   tb.add(g->opt, op, on);
   RC(upload_tables(g->d_fit_tables, tb.tab, st));
   CU(g->d_partials.ensure((size_t)part_total));
-  // wide tensor-core buckets: one activation stash per CTA (buckets launch one after the other and share it)
+  // wide tensor-core buckets: one activation stash + dW scratch per SM (buckets launch one after the other and share it)
   size_t stash_total = 0;
   g->stash_stride = 0;
   for (int b = 5; b < kBuckets; ++b)
     if (g->tc_fit[b].blocks > 0) g->stash_stride = std::max(g->stash_stride, tc_fit_stash_bytes(16 * b, g->tc_L[b]));
-  for (int b = 5; b < kBuckets; ++b) stash_total = std::max(stash_total, (size_t)g->tc_fit[b].blocks * g->stash_stride);
+  if (g->stash_stride > 0) stash_total = (size_t)kWideStashSlots * g->stash_stride;  // indexed by %smid, not by CTA
   if (stash_total > 0) CU(g->d_stash.ensure(stash_total));
   CU(g->d_loss_partials.ensure((size_t)slice_total));
   CU(g->d_loss_scratch.ensure((size_t)g->n_nets));
@@ -353,6 +354,7 @@ int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uin
   a.wpack = g->d_wpack.p;
   a.stash = g->d_stash.p;
   a.stash_stride = g->stash_stride;
+  a.stash_slots = kWideStashSlots;
   if (g->simt_fit.blocks > 0) {
     a.work_prefix = g->d_fit_tables.p + g->simt_fit.off_prefix;
     a.work_net = g->d_fit_tables.p + g->simt_fit.off_net;

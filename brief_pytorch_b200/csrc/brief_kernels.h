@@ -47,8 +47,9 @@ struct FitArgs {
   float* partials;       // per-slice gradient slots (padded device layout)
   float* loss_partials;  // per-slice loss terms
   const unsigned char* wpack;
-  unsigned char* stash;     // wide tensor-core kernel: per-CTA activation stash (stash_stride bytes per CTA)
+  unsigned char* stash;     // wide tensor-core kernel: per-SM activation stash + dW scratch (stash_stride bytes per SM id)
   size_t stash_stride;
+  int stash_slots;          // SM ids covered by `stash`
 };
 
 // Optimiser step over the whole group (one launch).

@@ -106,7 +106,12 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 1, kTile)) = make_uint4(0, 0, 0, 0);
   float* part = a.partials + n.part_off + (long long)slice * n.P_dev;
   for (int i = t; i < (n.P_dev >> 2); i += kWideThreads) reinterpret_cast<float4*>(part)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  unsigned char* stash = a.stash + (size_t)blockIdx.x * a.stash_stride;  // a_j (j <= NH-2) at stash + j * BUF
+  // per-SM scratch (one wide CTA is resident per SM: the slot of this SM is ours until the CTA exits), so its size does
+  // not grow with the grid and later CTAs of a multi-wave launch reuse lines that are already in L2
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (smid >= (unsigned int)a.stash_slots) __trap();
+  unsigned char* stash = a.stash + (size_t)smid * a.stash_stride;  // a_j (j <= NH-2) at stash + j * BUF
   float4* scr = reinterpret_cast<float4*>(stash + (size_t)(NH >= 2 ? NH - 1 : 0) * BUF);  // running dW sums, see below
 
   const uint32_t tm = tmem_base_s;
