@@ -137,17 +137,18 @@ def test_divided_fit_writes_a_directory_the_oracle_decodes(tmp_path, prec):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,steps", [((16, 48, 48), 20), ((96, 192, 192), 6)])
-def test_block_ownership_does_not_change_a_blocks_result(shape, steps):
+@pytest.mark.parametrize("shape,steps,ratio", [((16, 48, 48), 20, 16), ((96, 192, 192), 6, 2048), ((16, 48, 48), 8, 0.15)])
+def test_block_ownership_does_not_change_a_blocks_result(shape, steps, ratio):
     """with per-network slicing (reproducible=True) a block's fitted parameters are bit-identical
     whichever rank owns it / whatever shares the GPU.  The second case has random-point blocks of 96x96x96 voxels
-    (batch 100000 -> several slices per network, on-device sampler keyed by the block's global index)."""
+    (batch 100000 -> several slices per network, on-device sampler keyed by the block's global index); the third has
+    f = 77 networks, i.e. the wide tensor-core fit kernel."""
     from brief_pytorch_b200 import synth
     from brief_pytorch_b200.CompressFramework import NFGR
     from brief_pytorch_b200.group import pack_module_params
     o = opt()
     o["Compress"]["divide"]["divide_type"] = "total_1_2_2"
-    o["Compress"]["param"]["filesize_ratio"] = 16 if shape[0] == 16 else 2048
+    o["Compress"]["param"]["filesize_ratio"] = ratio
     o["Compress"]["checkpoints"] = "none"
     vol = synth.vessel(shape, seed=7)
     all_blocks, _ = NFGR(o, 0, "f16", reproducible=True).compress_divide(vol, None, max_steps=steps)

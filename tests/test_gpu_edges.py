@@ -142,20 +142,22 @@ def test_zero_length_and_error_paths():
 
 
 @pytest.mark.parametrize("prec", ["fp32", "f16"])
-def test_2d_image_fit_matches_oracle(prec):
-    """coords_channel = 2 (PNG/JPG path of the reference): channel order (h, w), whole-image batch."""
+@pytest.mark.parametrize("features", [32, 72])
+def test_2d_image_fit_matches_oracle(features, prec):
+    """coords_channel = 2 (PNG/JPG path of the reference): channel order (h, w), whole-image batch; a width of the fused
+    fit kernel and one of the wide kernel."""
     from brief_pytorch_b200.group import NetSpec, SirenGroup, pack_module_params
     rng = np.random.default_rng(12)
     dims = (37, 29)
     img = rng.integers(0, 255, size=dims + (1,), dtype=np.uint8)
-    kw = dict(coords_channel=2, layers=5, w0=30, features=32)
+    kw = dict(coords_channel=2, layers=5, w0=30, features=features)
     torch.manual_seed(9)
     ora = O.init_phi(dict(kw, data_channel=1, name="SIREN"))
     data_t, side = O.normalize_data(img.copy(), "minmaxany_0_100")
     coords = O.create_flattened_coords(dims, "-1,1")
     loss_ref, _, grads_ref, _ = O.loss_and_grads(O.siren_params(ora), coords, data_t.reshape(-1, 1),
                                                  torch.ones(img.size, 1), 0.0, kw["w0"])
-    grp = make_group([NetSpec(32, 5, 30.0, dims, 2)], prec)
+    grp = make_group([NetSpec(features, 5, 30.0, dims, 2)], prec)
     grp.set_axes(0, "-1,1")
     grp.set_params(0, pack_module_params(ora))
     t = torch.from_numpy(np.ascontiguousarray(img[..., 0])).cuda()
