@@ -34,12 +34,13 @@ for case in range(n_cases):
             vols.append(v)
             grp.bind_volume(j, v, 100.0, 29999.0, np_dtype="uint16", rules=[(10001, 65535, 0.1)], tau=55.0)
             grp.set_sampler(j, modes[j], batches[j])
-        losses = []
+        losses, grads = [], None
         for s in range(steps):
             losses.append(grp.fit_step(None, seed=5, step=s).cpu().numpy())
+            if s == 0:  # gradients are compared on IDENTICAL parameters only: one Adamax step moves every parameter by
+                grads = [grp.get_grads(j) for j in range(nets)]  # +-lr, and a near-zero gradient may differ in sign
             if s + 1 < steps:
                 grp.opt_step("Adamax", 1e-3)
-        grads = [grp.get_grads(j) for j in range(nets)]
         dec = [t.cpu().numpy() for t in grp.decompress("float32")]
         res[prec] = (np.stack(losses), grads, dec)
         grp.close()
@@ -52,7 +53,9 @@ for case in range(n_cases):
     eg = max(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) for a, b in zip(g16, g32))
     ed = max(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) for a, b in zip(d16, d32))
     worst = max(worst, el, eg, ed)
-    flag = "" if max(el, eg, ed) < 3e-2 and np.isfinite(l16).all() else "   <<<<<< CHECK"
+    # loss and step-0 gradients at the f16 tolerances of the parity tests; the decode after 1-3 optimiser steps sits on
+    # two slightly different parameter sets (see above) and is only reported
+    flag = "" if el < 1e-2 and eg < 5e-2 and np.isfinite(l16).all() and np.isfinite(ed) else "   <<<<<< CHECK"
     print(f"case {case}: L={L} f={fs} dims={dims} modes={[m[6:] for m in modes]} batch={batches} steps={steps}: "
-          f"loss {el:.1e} grad {eg:.1e} decode {ed:.1e}{flag}", flush=True)
+          f"loss {el:.1e} grad(step 0) {eg:.1e} decode {ed:.1e}{flag}", flush=True)
 print("worst relative deviation f16 vs fp32 kernels:", worst)
