@@ -16,18 +16,18 @@ using namespace umma;
 //                   ahead in the forward pass and one stage ahead in the backward pass (the backward pass ends with
 //                   W_1, W_2 resident — exactly what the next tile's forward pass starts with);
 //   * activations:  two [128 x F] buffers (a_j in buffer j & 1).  The forward epilogue also writes a_j (j <= NH-2) in
-//                   operand layout to a per-CTA STASH in global memory (L2-resident: 4 x 32 KB per CTA), from where
-//                   the backward pass brings it back with one bulk copy per stage;
-//   * dW:           accumulators of F columns, M = 128 (lane = input feature, column = output feature, so that a warp
-//                   touches 32 consecutive floats of a weight row).  The five hidden layers of an L = 7 network would
-//                   need 640 TMEM columns beside theta and dX, so the sums over the slice live in three places:
-//                   dW_3 in its own TMEM accumulator (lane = input feature), and the others (lane = output feature) are
-//                   added per tile into a per-CTA scratch in L2 by a plain
-//                   16-byte read-add-write whose reads are issued a whole stage early; the scratch is laid out so that
-//                   a warp's access is 512 contiguous bytes (every element belongs to one thread; fixed tile order, so
-//                   the fp32 sums are deterministic).  The slice's partial slot is written once, at the end.
+//                   operand layout to a per-SM STASH in global memory (L2-resident: 4 x 32 KB per SM; one wide CTA
+//                   is resident per SM, so the slot is indexed by %smid), from where the backward pass brings it back
+//                   with one bulk copy per stage;
+//   * dW:           per-tile accumulators of F columns, M = 128.  The five hidden layers of an L = 7 network would need
+//                   640 TMEM columns beside theta and dX, so the sums over the slice live in two places: dW_3 in its
+//                   own TMEM accumulator (lane = input feature), and the others (lane = output feature) are added per
+//                   tile into a per-SM scratch in L2 by a plain 16-byte read-add-write whose reads are issued a whole
+//                   stage early; the scratch is laid out so that a warp's access is 512 contiguous bytes.  Every
+//                   element belongs to one thread and the tile order is fixed, so the fp32 sums are deterministic.
+//                   The slice's partial slot is written once, at the end.
 // Two threads per sample row (column halves), stages run back to back with CTA barriers: the MMA of a stage, its
-// epilogue and the drain are not overlapped with each other (only the bulk copies run ahead).  Same numerics as the
+// epilogue and the dW update are not overlapped with each other (only the bulk copies and the scratch reads run ahead).  Same numerics as the
 // narrow kernel (fp16 operands, fp32 accumulation, hi/lo layer 0, kGradScale).
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
