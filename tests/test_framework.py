@@ -137,6 +137,41 @@ def test_divided_fit_writes_a_directory_the_oracle_decodes(tmp_path, prec):
 
 
 @pytest.mark.gpu
+def test_by_var_group_mixes_fused_and_wide_kernels(tmp_path):
+    """hipct.yaml's allocation (budgets proportional to block variance) gives every block its own width: here 25 .. 88, i.e.
+    two buckets of the fused tensor-core fit kernel and two of the wide one in ONE group.  The written directory is decoded
+    by the oracle to the same voxels (f16 tolerance) and the fit lowered every block's loss."""
+    from brief_pytorch_b200 import synth
+    from brief_pytorch_b200.CompressFramework import NFGR
+    o = opt()
+    o["Compress"]["divide"].update(divide_type="total_2_2_2", param_alloc="by_var")
+    o["Compress"]["param"]["filesize_ratio"] = 0.4
+    o["Compress"]["checkpoints"] = "none"
+    vol = synth.hipct((32, 64, 64), seed=5)
+    cf = NFGR(o, 0, "auto")
+    cdir = str(tmp_path / "compressed")
+    first, _ = NFGR(copy.deepcopy(o), 0, "auto").compress_divide(vol, None, max_steps=1)
+    blocks, _ = cf.compress_divide(vol, cdir, max_steps=60)
+    widths = sorted({b.features for b in blocks})
+    assert widths[0] <= 30 and widths[-1] >= 80, widths
+    for b0, b in zip(first, blocks):
+        assert np.isfinite(b.loss) and b.loss < b0.loss
+    ours = cf.decompress_divide(os.path.join(cdir, "sideinfos.yaml"), os.path.join(cdir, "module"),
+                                os.path.join(cdir, "sideinfos"))
+    chunks = []
+    for b in blocks:
+        with open(os.path.join(cdir, "sideinfos", b.name, "sideinfos.yaml")) as fh:
+            side = yaml.safe_load(fh)
+        m = O.init_phi(dict(o["Module"]["phi"], features=side["phi_features"]))
+        O.load_model(m, os.path.join(cdir, "module", b.name, "module"))
+        chunks.append({"data": O.decompress_block(m, side, "minmaxany_0_100"), "name": b.name, "d": b.d, "h": b.h, "w": b.w})
+    ref = O.merge_divided_data(chunks, list(vol.shape))
+    span = float(vol.max()) - float(vol.min())
+    d = np.abs(ours.astype(np.int64) - ref.astype(np.int64)).max()
+    assert d <= np.ceil(3 * 1e-2 * span) + 1, d
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("shape,steps,ratio", [((16, 48, 48), 20, 16), ((96, 192, 192), 6, 2048), ((16, 48, 48), 8, 0.15)])
 def test_block_ownership_does_not_change_a_blocks_result(shape, steps, ratio):
     """with per-network slicing (reproducible=True) a block's fitted parameters are bit-identical
