@@ -12,6 +12,12 @@ network (gather + forward + weighted L2 + backward + Adamax).  For N>1 every ran
 (one such volume per GPU: weak scaling), no collective on the fit path; per-block loss statistics are all-gathered
 after the timed region.
 
+Named shapes of BASELINE.json configs 3-5 (`--workload neuron1024 | neuron1024_nb4 | hipct2048 | hipct2048_equal |
+decomp4096 | decomp4096_f39`): ONE volume of that shape, generated block by block on the device, its blocks sharded over
+the `--gpus N` ranks by parameter-weighted LPT (strong scaling; no collective on the fit or decode path), with per-rank
+busy time and LPT imbalance in the line.  The default run also carries a small strong-scaling leg
+(`strong_scaling`) and one short measurement per block geometry (`workloads`).
+
 One JSON line on stdout (rank 0); see README/DESIGN.md for the keys.
 """
 import argparse
@@ -58,6 +64,36 @@ WORKLOADS = {
     "hipct256": ((256, 512, 512), 128, 4, 7, 10.0, 100000,
                  "DivideTask hipct.yaml geometry (2048^3 ratio 128, Nb=512): 256^3 blocks, SIREN L=7 f=113 w0=10, "
                  "randompoint batch 100000/block, Adamax; 4 blocks per GPU (wide tcgen05 fit kernel: streamed weights, stashed activations)"),
+}
+
+
+# ONE volume of the named shape, blocks sharded over the ranks (strong scaling).  kind = synth_device generator.
+NAMED = {
+    "neuron1024": dict(kind="neuron", shape=(1024, 1024, 1024), ratio=512, nb=-1, alloc="by_size", thres=100, layers=7, w0=10.0,
+                       rules=[(10001, 65535, 0.1)], fit=True,
+                       desc="DivideTask neuron.yaml on a synthetic 1024^3 u16 volume, ratio 512, divide adaptotal_-1_-1_-1_-1 (auto Nb = "
+                            "param bytes / (4*1361) = 770 -> grid 8x8x8 = 512 blocks 128^3, SIREN L=7 f=19), by_size budgets, weight "
+                            "rule value_10001_65535_0.1, randompoint batch 100000/block, Adamax"),
+    "neuron1024_nb4": dict(kind="neuron", shape=(1024, 1024, 1024), ratio=512, nb=4, alloc="by_size", thres=100, layers=7, w0=10.0,
+                           rules=[(10001, 65535, 0.1)], fit=True,
+                           desc="DivideTask neuron.yaml AS SHIPPED (Nb=4) on a synthetic 1024^3 u16 volume: 4 blocks 1024x512x512, "
+                                "SIREN L=7 f=228 (F_PAD > 128: fp32 CUDA-core fit kernels), randompoint batch 100000/block, Adamax"),
+    "hipct2048": dict(kind="hipct", shape=(2048, 2048, 2048), ratio=128, nb=512, alloc="by_var", thres=26, layers=7, w0=10.0,
+                      rules=[(65535, 65535, 1.0)], fit=True,
+                      desc="DivideTask hipct.yaml on a synthetic 2048^3 u16 volume, ratio 128, Nb=512 -> 512 blocks 256^3, by_var "
+                           "budgets (per-block widths around f=113), randompoint batch 100000/block, Adamax"),
+    "hipct2048_equal": dict(kind="hipct", shape=(2048, 2048, 2048), ratio=128, nb=512, alloc="equal", thres=26, layers=7, w0=10.0,
+                            rules=[(65535, 65535, 1.0)], fit=True,
+                            desc="hipct.yaml geometry (2048^3, ratio 128, Nb=512 -> 512 blocks 256^3) with EQUAL budgets: every block "
+                                 "f=113 (wide tcgen05 fit kernel), randompoint batch 100000/block, Adamax"),
+    "decomp4096": dict(kind=None, shape=(4096, 4096, 4096), ratio=128, nb=4096, alloc="equal", thres=26, layers=7, w0=10.0,
+                       rules=[], fit=False,
+                       desc="Decompress-only sweep: 4096^3 u16 output grid from 4096 stored per-block SIRENs (256^3 blocks, L=7 "
+                            "f=113, reference initialisation), output kept sharded by block owner"),
+    "decomp4096_f39": dict(kind=None, shape=(4096, 4096, 4096), ratio=128, nb=32768, alloc="equal", thres=26, layers=7, w0=10.0,
+                           rules=[], fit=False,
+                           desc="Decompress-only sweep: 4096^3 u16 output grid from 32768 stored per-block SIRENs (128^3 blocks, "
+                                "L=7 f=39), output kept sharded by block owner"),
 }
 
 
@@ -196,18 +232,401 @@ def run_reference(args, plan):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+
+# ======================================================================================================================
+# named shapes: ONE volume, blocks sharded over the ranks by LPT (strong scaling)
+# ======================================================================================================================
+def _dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def plan_named(cfg, dev, rank, world):
+    """Partition + budgets + widths of a named volume exactly as the reference sizes them (cal_divide_num, divide_data's
+    block ranges, alloc_param, SIREN.calc_features).  by_var needs every block's variance: each rank generates the blocks
+    of an even share, takes their sums with ONE brief_block_stats launch, and the table is all-gathered."""
+    import torch.distributed as dist
+    from brief_pytorch_b200 import misc, sharding, synth_device
+    from brief_pytorch_b200.group import block_stats
+    from brief_pytorch_b200.Networks import SIREN
+    shape = cfg["shape"]
+    param_bytes = int(np.prod(shape)) * 2 / cfg["ratio"]
+    grid = [int(x) for x in misc.cal_divide_num(*shape, cfg["nb"], param_bytes)]
+    ext = [shape[k] // grid[k] for k in range(3)]
+    assert all(ext[k] * grid[k] == shape[k] for k in range(3))
+    ranges = [((iz * ext[0], iy * ext[1], ix * ext[2]), ((iz + 1) * ext[0], (iy + 1) * ext[1], (ix + 1) * ext[2]))
+              for iz in range(grid[0]) for iy in range(grid[1]) for ix in range(grid[2])]
+    n_blocks = len(ranges)
+    size = int(np.prod(ext))
+    chunks = [{"size": size, "total_size": size * n_blocks, "name": i} for i in range(n_blocks)]
+    t_var = 0.0
+    if cfg["alloc"] == "by_var":
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        table = torch.zeros((n_blocks, 2), dtype=torch.float64, device=dev)
+        for i in range(rank, n_blocks, world):
+            blk = synth_device.block(cfg["kind"], shape, ranges[i][0], ranges[i][1], 42, i, dev)
+            st = block_stats([blk], "uint16")
+            table[i, 0], table[i, 1] = float(st[0, 2]), float(st[0, 3])
+        if world > 1:
+            dist.all_reduce(table)
+        torch.cuda.synchronize()
+        t_var = time.perf_counter() - t0
+        for c, row in zip(chunks, table.cpu().numpy()):
+            c["var"] = misc.variance_from_sums(float(row[0]), float(row[1]), size)
+    chunks = misc.alloc_param(chunks, param_bytes, cfg["alloc"], cfg["thres"])
+    feats = {}
+    for c in chunks:
+        feats[c["name"]] = SIREN.calc_features(param_count=c["param_size"] / 4.0, coords_channel=3, data_channel=1, layers=cfg["layers"])
+    ids = sorted(feats)
+    batch = size if size <= 80 ** 3 else 100000
+    costs = [sharding.block_cost(feats[i], cfg["layers"], batch, 80000) for i in ids]
+    owner = sharding.lpt_assign(costs, world)
+    return dict(grid=grid, ext=tuple(ext), ranges=ranges, ids=ids, feats=feats, owner=owner, costs=costs, batch=batch,
+                full_block=size <= 80 ** 3, n_blocks_total=n_blocks, t_var=t_var)
+
+
+def run_named(args):
+    """`--workload <named shape>`: see measure_named."""
+    cfg = NAMED[args.workload]
+    rank, world, local = _dist_env()
+    if args.impl == "reference":
+        return run_reference_named(args, cfg)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    if args.steps == 1000 and args.warmup == 50:
+        args.steps, args.warmup = 10, 3
+    line = measure_named(cfg, args, dev, rank, world, local)
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_named(cfg, args, dev, rank, world, local):
+    """One volume of a named shape (BASELINE configs 3-5) sharded over the ranks: fit throughput (device-timed, max over
+    ranks) and decompress throughput with the output kept sharded by block owner.  Returns the JSON line on rank 0."""
+    import zlib
+    import torch.distributed as dist
+    from brief_pytorch_b200 import sharding, synth_device
+    from brief_pytorch_b200.group import NetSpec, SirenGroup, launch_count, pack_module_params, reset_launch_count
+    from brief_pytorch_b200.Networks import init_phi
+    pk = peaks()
+    P = plan_named(cfg, dev, rank, world)
+    mine = [k for k, i in enumerate(P["ids"]) if P["owner"][k] == rank]
+    feats = [P["feats"][P["ids"][k]] for k in mine]
+    specs = [NetSpec(f, cfg["layers"], cfg["w0"], P["ext"]) for f in feats]
+    t0 = time.perf_counter()
+    grp = SirenGroup(specs, dev, args.precision) if specs else None
+    if grp is not None:
+        grp.set_slicing(args.reproducible)
+    keep = []
+    cache = {}
+    for j, k in enumerate(mine):
+        i = P["ids"][k]
+        f = feats[j]
+        if f not in cache:  # reference initialisation (seed 42 -> init_phi), one draw per width like the reference's per-block processes
+            torch.manual_seed(42)
+            cache[f] = pack_module_params(init_phi(dict(name="SIREN", coords_channel=3, data_channel=1, layers=cfg["layers"],
+                                                        w0=cfg["w0"], features=f)))
+        grp.set_params(j, cache[f])
+        grp.set_stream(j, i)
+        if not cfg["fit"]:
+            grp.set_denorm(j, 1000.0, 40000.0, 0.0, 100.0)
+        if cfg["fit"]:
+            blk = synth_device.block(cfg["kind"], cfg["shape"], P["ranges"][i][0], P["ranges"][i][1], 42, i, dev)
+            keep.append(blk)
+    vox_local = len(mine) * int(np.prod(P["ext"]))
+    fit = None
+    precs = sorted({grp.precision(j) for j in range(len(mine))}) if grp is not None else []
+    if cfg["fit"] and grp is not None:
+        from brief_pytorch_b200.group import block_stats
+        st = block_stats(keep, "uint16")
+        for j in range(len(mine)):
+            vmin, vmax = float(st[j, 0]), float(st[j, 1])
+            tau = (65535.0 - vmin) / max(vmax - vmin, 1.0) * 100.0
+            grp.bind_volume(j, keep[j], vmin, vmax if vmax > vmin else vmin + 1.0, 0.0, 100.0, rules=cfg["rules"], tau=tau, np_dtype="uint16")
+            grp.set_sampler(j, "randomcube" if P["full_block"] else "randompoint", P["batch"])
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    opt_kw = dict(kind="Adamax", lr=1e-3, milestones=(50000, 60000, 70000), gamma=0.2, seed=42)
+    clocks = ClockSampler(local)
+    t_fit = 0.0
+    checksum = 0
+    if cfg["fit"]:
+        if grp is not None:
+            grp.fit_run(args.warmup, **opt_kw)
+        barrier()
+        clocks.start()
+        reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        if grp is not None:
+            grp.fit_run(args.steps, **opt_kw)  # blocks of a real volume stay resident across steps: no flush (inputs >> L2 anyway)
+        e1.record()
+        barrier()
+        t_fit = e0.elapsed_time(e1) / 1e3
+        if args.reproducible:
+            for j, k in enumerate(mine):
+                checksum ^= zlib.crc32(grp.get_params(j).tobytes() + int(P["ids"][k]).to_bytes(4, "little"))
+    else:
+        clocks.start()
+    launches = launch_count() if cfg["fit"] else 0
+
+    # ---- decompress: every own block, output kept on the owner (sharded volume) ----
+    reset_launch_count()
+    t_dec = 0.0
+    out_bytes = vox_local * 2
+    if grp is not None:
+        free, _ = torch.cuda.mem_get_info(dev)
+        slab = len(mine)
+        while slab > 1 and slab * int(np.prod(P["ext"])) * 2 > free - (6 << 30):
+            slab = (slab + 1) // 2
+        outs = [torch.empty(P["ext"], dtype=torch.int16, device=dev) for _ in range(slab)]
+        resident = slab == len(mine)
+        grp.decompress("uint16", out=outs + [None] * (len(mine) - slab), nets=range(min(slab, 4)))  # warm-up (pack + a few blocks)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for lo in range(0, len(mine), slab):
+            ids = list(range(lo, min(lo + slab, len(mine))))
+            full = [None] * len(mine)
+            for q, j in enumerate(ids):
+                full[j] = outs[q]
+            grp.decompress("uint16", out=full, nets=ids)
+        d1.record()
+        barrier()
+        t_dec = d0.elapsed_time(d1) / 1e3
+    else:
+        barrier(); barrier()
+        resident = True
+    dec_launches = launch_count()
+    clk = clocks.stop()
+
+    samples_local = len(mine) * P["batch"] * args.steps if cfg["fit"] else 0
+    fit_flops_local = sum(sharding.fit_flops_per_sample(f, cfg["layers"]) for f in feats) * P["batch"] * args.steps if cfg["fit"] else 0
+    fwd_flops_local = sum(sharding.forward_flops_per_sample(f, cfg["layers"]) for f in feats) * int(np.prod(P["ext"]))
+    mine_cost = sum(P["costs"][k] for k in mine)
+    vals = torch.tensor([t_fit, t_dec, samples_local, vox_local, launches, fit_flops_local, fwd_flops_local, mine_cost, t_setup,
+                         float(len(mine)), float(checksum)], dtype=torch.float64, device=dev)
+    if world > 1:
+        allv = [torch.empty_like(vals) for _ in range(world)]
+        dist.all_gather(allv, vals)
+        allv = torch.stack(allv).cpu().numpy()
+    else:
+        allv = vals.cpu().numpy()[None]
+    if rank == 0:
+        tf, td = allv[:, 0], allv[:, 1]
+        tmax_fit, tmax_dec = float(tf.max()), float(td.max())
+        total_samples, total_vox = float(allv[:, 2].sum()), float(allv[:, 3].sum())
+        widths = sorted(P["feats"].values())
+        cks = 0
+        for c in allv[:, 10]:
+            cks ^= int(c)
+        line = {
+            "metric": METRIC if cfg["fit"] else "siren_decompress_voxels_per_s",
+            "value": (total_samples / tmax_fit) if cfg["fit"] else (total_vox / tmax_dec),
+            "unit": UNIT if cfg["fit"] else "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (1e3 * tmax_fit / args.steps) if cfg["fit"] else 1e3 * tmax_dec,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16" if precs == ["f16"] else ("f32" if precs == ["fp32"] else "f16+f32"), "data": "synthetic",
+            "config": {"workload": cfg["desc"], "volume": list(cfg["shape"]), "grid": P["grid"], "block_shape": list(P["ext"]),
+                       "blocks": len(P["ids"]), "blocks_dropped_by_thres": P["n_blocks_total"] - len(P["ids"]),
+                       "features_min_median_max": [int(widths[0]), int(widths[len(widths) // 2]), int(widths[-1])],
+                       "layers": cfg["layers"], "batch_per_block": P["batch"], "param_alloc": cfg["alloc"],
+                       "l2": "inputs larger than L2 (raw blocks of the rank >> 126 MB); no flush between steps",
+                       "parallelism": f"blocks of ONE volume sharded by parameter-weighted LPT over {world} GPU(s); no collective on the fit or decode path",
+                       "reproducible_slicing": bool(args.reproducible)},
+            "gpu_launches": int(allv[:, 4].sum()) + dec_launches * world,
+            "per_rank": {"blocks": [int(x) for x in allv[:, 9]], "fit_busy_ms_per_step": [round(1e3 * float(x) / max(args.steps, 1), 4) for x in tf],
+                         "decompress_busy_ms": [round(1e3 * float(x), 3) for x in td],
+                         "lpt_cost_share": [round(float(x) / max(float(allv[:, 7].sum()), 1e-30), 5) for x in allv[:, 7]],
+                         "setup_s": [round(float(x), 2) for x in allv[:, 8]]},
+            "imbalance": {"fit_max_over_mean": float(tf.max() / max(tf.mean(), 1e-30)) if cfg["fit"] else None,
+                          "decompress_max_over_mean": float(td.max() / max(td.mean(), 1e-30)),
+                          "lpt_cost_max_over_mean": float(allv[:, 7].max() / max(allv[:, 7].mean(), 1e-30))},
+            "decompress": {"value": total_vox / tmax_dec, "unit": "voxels/s", "ms": 1e3 * tmax_dec,
+                           "hbm_gbs": total_vox * 2 / tmax_dec / 1e9, "hbm_frac": total_vox * 2 / tmax_dec / 1e9 / (pk["hbm_gbs"] * world),
+                           "tflops": float(allv[:, 6].sum()) / tmax_dec / 1e12,
+                           "tensor_frac": float(allv[:, 6].sum()) / tmax_dec / 1e12 / (pk["bf16_tflops"] * world),
+                           "output": "sharded by block owner" + ("" if resident else ", decoded slab by slab into a reused buffer"),
+                           "output_bytes_total": int(total_vox * 2)},
+            "clocks": clk,
+        }
+        if cfg["fit"]:
+            tf_total = float(allv[:, 5].sum()) / tmax_fit / 1e12
+            line["roofline"] = {"bound": "tensor", "achieved": tf_total, "peak": pk["bf16_tflops_sustained"] * world, "unit": "TFLOP/s",
+                                "frac": tf_total / (pk["bf16_tflops_sustained"] * world), "traffic": None,
+                                "peak_src": pk["src"] + " bf16 sustained x n_gpus (kernel timed inside a long step loop)",
+                                "kernel": "whole step (fit kernels of every width bucket + optimiser), algorithmic FLOPs of all blocks"}
+            line["e2e"] = None
+            line["by_var_stats_s"] = P["t_var"]
+        else:
+            line["roofline"] = {"bound": "hbm", "achieved": total_vox * 2 / tmax_dec / 1e9, "peak": pk["hbm_gbs"] * world, "unit": "GB/s",
+                                "frac": total_vox * 2 / tmax_dec / 1e9 / (pk["hbm_gbs"] * world), "traffic": None,
+                                "peak_src": pk["src"] + " copy bandwidth x n_gpus",
+                                "note": "asked for against HBM; the binding unit is the SFU ((L-1) f sines per voxel), see DESIGN.md 4.2"}
+        if args.reproducible:
+            line["param_checksum"] = f"{cks:08x}"
+        return line
+    return None
+
+
+def run_reference_named(args, cfg):
+    """--impl reference for a named shape: the oracle's CPU loop on ONE block of the volume's typical width."""
+    rank, world, local = _dist_env()
+    if rank != 0:
+        return
+    from brief_pytorch_b200 import misc
+    from brief_pytorch_b200.Networks import SIREN
+    shape = cfg["shape"]
+    param_bytes = int(np.prod(shape)) * 2 / cfg["ratio"]
+    grid = [int(x) for x in misc.cal_divide_num(*shape, cfg["nb"], param_bytes)]
+    n_blocks = grid[0] * grid[1] * grid[2]
+    ext = tuple(shape[k] // grid[k] for k in range(3))
+    f = SIREN.calc_features(param_count=param_bytes / n_blocks / 4.0, coords_channel=3, data_channel=1, layers=cfg["layers"])
+    sample_shape = tuple(min(e, 128) for e in ext)  # the oracle materialises 20 B/voxel of fp32 copies: bound the block
+    plan = dict(block_shape=sample_shape, layers=cfg["layers"], w0=cfg["w0"], features=f, batch=100000, full_block=False,
+                desc=cfg["desc"])
+    if not cfg["fit"]:
+        emit({"impl": "reference", "unavailable": "decompress-only workload: the reference arm times the fit metric"})
+        return
+    if args.steps == 1000 and args.warmup == 50:
+        args.steps, args.warmup = 10, 3
+    run_reference(args, plan)
+
+
+def quick_workload(name, dev, precision, pk, flush, steps=60, warmup=10):
+    """One short device-resident measurement of a block geometry (the per-GPU share of a WORKLOADS entry): step rate with
+    the L2 flushed between steps, the fit kernel(s) alone for the roofline fraction, and the decode rate."""
+    from brief_pytorch_b200 import sharding, synth_device
+    from brief_pytorch_b200.group import NetSpec, SirenGroup, block_stats, pack_module_params
+    from brief_pytorch_b200.Networks import init_phi
+    plan = plan_blocks(name)
+    bs, gd = plan["block_shape"], plan["grid"]
+    n = plan["n_blocks"]
+    grp = SirenGroup([NetSpec(plan["features"], plan["layers"], plan["w0"], bs) for _ in range(n)], dev, precision)
+    torch.manual_seed(42)
+    p0 = pack_module_params(init_phi(dict(name="SIREN", coords_channel=3, data_channel=1, layers=plan["layers"], w0=plan["w0"],
+                                          features=plan["features"])))
+    keep = []
+    for k in range(n):
+        iz, iy, ix = k // (gd[1] * gd[2]), (k // gd[2]) % gd[1], k % gd[2]
+        lo = (iz * bs[0], iy * bs[1], ix * bs[2])
+        keep.append(synth_device.block("vessel", plan["shape"], lo, tuple(lo[i] + bs[i] for i in range(3)), 42, k, dev))
+    st = block_stats(keep, "uint16")
+    for k in range(n):
+        vmin, vmax = float(st[k, 0]), float(st[k, 1])
+        grp.set_params(k, p0)
+        grp.bind_volume(k, keep[k], vmin, vmax, 0.0, 100.0, rules=[(65535, 65535, 1.0)], tau=(65535.0 - vmin) / (vmax - vmin) * 100.0,
+                        np_dtype="uint16")
+        grp.set_sampler(k, "randomcube" if plan["full_block"] else "randompoint", plan["batch"])
+    opt_kw = dict(kind="Adamax", lr=1e-3, milestones=(50000, 60000, 70000), gamma=0.2, seed=42)
+    grp.fit_run(warmup, **opt_kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_step = t_kern = 0.0
+    for s_ in range(steps):
+        flush.fill_(s_ & 0xFF)
+        e0.record(); grp.fit_run(1, **opt_kw); e1.record()
+        torch.cuda.synchronize()
+        t_step += e0.elapsed_time(e1) / 1e3
+    n_k = min(steps, 30)
+    for s_ in range(n_k):
+        flush.fill_(s_ & 0xFF)
+        e0.record(); grp.fit_kernel_only(seed=42, step=s_); e1.record()
+        torch.cuda.synchronize()
+        t_kern += e0.elapsed_time(e1) / 1e3
+    outs = grp.decompress("uint16")
+    torch.cuda.synchronize()
+    t_dec = 0.0
+    for s_ in range(3):
+        flush.fill_(s_)
+        e0.record(); grp.decompress("uint16", out=outs); e1.record()
+        torch.cuda.synchronize()
+        t_dec += e0.elapsed_time(e1) / 1e3
+    samples = n * plan["batch"]
+    flops = sharding.fit_flops_per_sample(plan["features"], plan["layers"])
+    tf = samples * flops / (t_kern / n_k) / 1e12
+    res = {"value": samples * steps / t_step, "unit": UNIT, "ms_per_step": 1e3 * t_step / steps, "blocks": n,
+           "block_shape": list(bs), "features": plan["features"], "layers": plan["layers"], "batch_per_block": plan["batch"],
+           "precision": grp.precision(0), "fit_kernel_ms": 1e3 * t_kern / n_k, "fit_tflops": tf,
+           "roofline_frac": tf / pk["bf16_tflops"], "decompress_voxels_per_s": n * int(np.prod(bs)) / (t_dec / 3)}
+    grp.close()
+    return res
+
+
+def gpu_eager_rate(plan, seconds, dev):
+    """The reference's REAL GPU path beside the CPU one: the same oracle loop (main.py:385-401 around stock torch ops, fp32,
+    eager) with module, data and sampler tensors on the B200 — cuBLAS sgemm + elementwise kernels, ~700 ATen ops per step,
+    index draw on the CPU and loss.item() every step like the reference.  One block of the workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import brief_oracle as O
+    from brief_pytorch_b200 import synth
+    bs = plan["block_shape"]
+    blk = synth.vessel(bs, seed=42)
+    data_t, side = O.normalize_data(blk.copy(), "minmaxany_0_100")
+    weight = O.parse_weight(blk.copy(), ["value_65535_65535_1"])
+    thr = O.weight_thres_normalized(65535, "minmaxany_0_100", side["min"], side["max"])
+    torch.manual_seed(42)
+    phi = O.init_phi(dict(coords_channel=3, data_channel=1, name="SIREN", layers=plan["layers"], w0=plan["w0"],
+                          features=plan["features"])).to(dev)
+    opt = O.configure_optimizer(phi.parameters(), "Adamax", 1e-3)
+    sch = O.configure_lr_scheduler(opt, {"name": "MultiStepLR", "milestones": [50000, 60000, 70000], "gamma": 0.2})
+    if plan["full_block"]:
+        sampler = O.RandomCubeSampler(data_t.to(dev), weight, "-1,1", 1, [10000000] * 3, 10 ** 9, device=str(dev), gpu_force=True)
+    else:
+        sampler = O.RandompointSampler(data_t.to(dev), weight, "-1,1", plan["batch"], 10 ** 9, device=str(dev))
+    it = iter(sampler)
+
+    def step():
+        c, d, w = next(it)
+        return float(O.train_step(phi, opt, sch, c, d, w, thr).detach())
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds and n < 2000:
+        step(); n += 1
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": plan["batch"] * n / dt, "unit": UNIT, "kind": "reference's own GPU path: oracle loop on torch-CUDA eager fp32 "
+            "(TF32 off), one block at a time, CPU index draw + loss.item() per step", "ms_per_step": 1e3 * dt / n,
+            "sample": f"{n} steps of one block (f={plan['features']}, batch {plan['batch']})"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="vessel", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="vessel", choices=sorted(WORKLOADS) + sorted(NAMED))
+    ap.add_argument("--reproducible", action="store_true",
+                    help="per-network slicing: every block's fitted parameters are bit-identical for any number of GPUs "
+                         "(the line carries a checksum of all fitted parameters to compare across N)")
+    ap.add_argument("--no-side-legs", action="store_true", help="skip the HBM side legs, per-geometry table and strong-scaling leg")
     ap.add_argument("--precision", default="auto", choices=["auto", "f16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload in NAMED:
+        return run_named(args)
     plan = plan_blocks(args.workload)
     if args.impl == "reference":
         if args.steps == 1000 and args.warmup == 50:
@@ -328,57 +747,37 @@ def main():
         host_loss = torch.empty(n_local, dtype=torch.float32).pin_memory()
         h2d, d2h = 0, n_local * 4
 
-    # step s+1's indices cross PCIe on a copy stream while step s computes (two device buffers); every step still moves
-    # its own h2d bytes and reads its own loss back before the next one starts
-    copy_stream = torch.cuda.Stream(device=dev)
-    main_stream = torch.cuda.current_stream(dev)
-    idx_buf = [torch.empty_like(dev_idx) for _ in range(2)] if host_idx is not None else None
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-
-    def prefetch(s):
-        if host_idx is None:
-            return
-        k = s & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[k])
-            idx_buf[k].copy_(host_idx[s % 8], non_blocking=True)
-            ready[k].record(copy_stream)
-
-    loss_buf = [torch.empty(n_local, dtype=torch.float32).pin_memory() for _ in range(2)]
-    loss_done = [torch.cuda.Event() for _ in range(2)]
+    # One C call per step (brief_fit_step_host): the step is ONE CUDA-graph launch — [h2d: step scalars + this step's
+    # pinned indices] -> fit -> optimiser -> [d2h: per-block loss] — and the host reads every step's loss, one step
+    # behind the GPU (the reference's loss.item() stalls the GPU every step, main.py:401).  Four pinned buffer sets cycle.
+    n_sets = 4
+    if host_idx is not None:
+        host_idx = host_idx[:n_sets]
+    loss_buf = [torch.zeros(n_local, dtype=torch.float32).pin_memory() for _ in range(n_sets)]
+    loss_done = [torch.cuda.Event() for _ in range(n_sets)]
     loss_seen = [0.0]
+    e2e_kw = dict(kind="Adamax", lr=1e-3, milestones=(50000, 60000, 70000), gamma=0.2, seed=42)
 
     def e2e_step(s):
-        """Step s is enqueued (indices h2d -> fit -> optimiser -> loss d2h), THEN the host waits for and reads the loss
-        of step s-1: every step's loss reaches the host, one step behind the GPU, so the launch latency of the next
-        step is not exposed (the reference's loss.item() stalls the GPU every step, main.py:401)."""
-        k = s & 1
-        prefetch(s + 1)
-        if host_idx is not None:
-            main_stream.wait_event(ready[k])
-        loss = grp.fit_step(idx_buf[k] if host_idx is not None else None, seed=42, step=s)
-        grp.opt_step("Adamax", 1e-3)
-        consumed[k].record(main_stream)
-        loss_buf[k].copy_(loss, non_blocking=True)
-        loss_done[k].record(main_stream)
+        k = s % n_sets
+        grp.fit_step_host(host_idx[k] if host_idx is not None else None, loss_buf[k], **e2e_kw)
+        loss_done[k].record()
         if s > 0:
-            loss_done[k ^ 1].synchronize()
-            loss_seen[0] = float(loss_buf[k ^ 1][0])  # the host really consumes the value
+            loss_done[(s - 1) % n_sets].synchronize()
+            loss_seen[0] = float(loss_buf[(s - 1) % n_sets][0])  # the host really consumes the value
         return loss_buf[k]
 
-    for k in range(2):
-        consumed[k].record(main_stream)
-    prefetch(0)
     for s in range(args.warmup):
         e2e_step(s)
     barrier()
+    reset_launch_count()
     t0 = time.perf_counter()
     for s in range(args.steps):
         e2e_step(s)
     barrier()
     t_e2e = time.perf_counter() - t0
-    final_loss = loss_buf[(args.steps - 1) & 1].clone()
+    e2e_launches = launch_count()
+    final_loss = loss_buf[(args.steps - 1) % n_sets].clone()
 
     # ---- decompress of every local block (secondary metric) ----
     outs = grp.decompress("uint16")
@@ -503,7 +902,42 @@ def main():
             ok = all(float(got[b].view(torch.int16).to(torch.int64).sum()) == float(want[b, 0]) for b in range(n_total))
             nbytes = sum(int(np.prod(bs)) * 2 for b in range(n_total) if owner[b] != 0)
             gather = {"ms": 1e3 * t_gather, "bytes_into_rank0": nbytes, "gbs": nbytes / t_gather / 1e9, "checksums_ok": ok}
+        # the same exchange at >= 1 GiB into the assembling rank (every block listed `rep` times): the NVLink-rate figure
+        rep = max(1, int(np.ceil((1.15 * (1 << 30)) / max(1, (world - 1) * n_local * int(np.prod(bs)) * 2))))
+        big_owner = [owner[b] for b in range(n_total) for _ in range(rep)]
+        big_local = {b * rep + i: outs[j] for j, b in enumerate(mine) for i in range(rep)}
+        big_shapes = [bs] * (n_total * rep)
+        sharding.gather_blocks(big_local, big_owner, big_shapes, dst=0, dtype=torch.int16)
+        barrier()
+        g0.record()
+        got_big = sharding.gather_blocks(big_local, big_owner, big_shapes, dst=0, dtype=torch.int16)
+        g1.record()
+        barrier()
+        if rank == 0:
+            nb_big = sum(int(np.prod(bs)) * 2 for b in big_owner if b != 0)
+            gather["large"] = {"ms": g0.elapsed_time(g1), "bytes_into_rank0": nb_big, "gbs": nb_big / (g0.elapsed_time(g1) / 1e3) / 1e9,
+                               "note": "one packed payload per sending rank, one grouped ncclSend/Recv; peer-copy reference 770 GB/s per direction"}
+        del got_big
         del got
+
+    # ---- one short measurement per block geometry of the BASELINE configs (rank 0's GPU; N = 1 run only) ----
+    workloads = None
+    if world == 1 and not args.no_side_legs:
+        workloads = {}
+        for name in sorted(WORKLOADS):
+            if name == args.workload:
+                continue
+            try:
+                workloads[name] = quick_workload(name, dev, args.precision, pk, flush)
+            except Exception as e:  # a geometry that cannot run must show up in the line, not abort the headline
+                workloads[name] = {"error": str(e)[:200]}
+
+    # ---- strong scaling: ONE 1024^3 neuron volume (BASELINE config 3, 512 blocks 128^3) sharded over the ranks by LPT ----
+    strong = None
+    if not args.no_side_legs:
+        from types import SimpleNamespace
+        strong = measure_named(NAMED["neuron1024"], SimpleNamespace(steps=10, warmup=3, precision=args.precision,
+                                                                    reproducible=args.reproducible), dev, rank, world, local)
 
     # ---- reduce over ranks (max time), gather per-block stats (the only collective; outside the timed region) ----
     times = torch.tensor([t_dev, t_b2b, t_e2e, t_kernel, t_dec, t_dec_e2e], dtype=torch.float64, device=dev)
@@ -533,9 +967,10 @@ def main():
                              "ms_per_step": 1e3 * t_b2b / args.steps, "note": "no L2 flush, one event pair around K steps"},
             "e2e": {"value": samples_per_step * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "note": "per step: pinned host sampler indices -> device (copy stream, one step ahead), fit_step + "
-                            "opt_step via the Python API, per-block loss -> pinned host buffer every step, read by the host one "
-                            "step behind the GPU"},
+                    "gpu_launches": int(e2e_launches),
+                    "note": "per step ONE call SirenGroup.fit_step_host = one CUDA-graph launch: [pinned host sampler indices + "
+                            "step scalars -> device] -> fit kernel -> optimiser kernel -> [per-block loss -> pinned host]; the "
+                            "host reads every step's loss, one step behind the GPU"},
             "gpu_launches": int(launches_total),
             "roofline": {"bound": "tensor", "achieved": tf_kernel, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": tf_kernel / peak_tf,
@@ -556,6 +991,18 @@ def main():
         line["preprocess"] = pre_stats
         if gather is not None:
             line["gather_decoded_blocks"] = gather
+        if workloads is not None:
+            workloads[args.workload] = {"value": value, "unit": UNIT, "ms_per_step": 1e3 * t_dev / args.steps, "blocks": n_local,
+                                        "block_shape": list(bs), "features": plan["features"], "layers": plan["layers"],
+                                        "batch_per_block": plan["batch"], "precision": prec, "fit_kernel_ms": 1e3 * t_kernel,
+                                        "fit_tflops": tf_kernel, "roofline_frac": tf_kernel / peak_tf,
+                                        "decompress_voxels_per_s": vox_total / t_dec}
+            line["workloads"] = workloads
+        if strong is not None:
+            line["strong_scaling"] = {k: strong[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "config", "per_rank", "imbalance",
+                                                             "decompress", "roofline") if k in strong}
+            if "param_checksum" in strong:
+                line["strong_scaling"]["param_checksum"] = strong["param_checksum"]
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             step = oracle_fit_rate(plan, args.cpu_seconds, threads)
@@ -568,6 +1015,10 @@ def main():
             line["cpu_baseline"] = {"value": plan["batch"] * n / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{n} steps of one block (f={plan['features']}, batch {plan['batch']}) "
                                               f"with the oracle's torch-CPU restatement of main.py:385-400"}
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_rate(plan, 4.0, dev)
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"error": str(e)[:200]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -65,6 +65,8 @@ PROTOTYPES = {
     "brief_fit_kernels": (c_i32, [c_vp, c_vp, c_u64, c_u64, c_vp]),
     "brief_opt_step": (c_i32, [c_vp, c_i32, c_f32, c_f32, c_f32, c_f32, c_i64, c_vp]),
     "brief_fit_run": (c_i32, [c_vp, C.POINTER(OptConfig), c_u64, c_i64, c_i64, c_vp, c_vp]),
+    "brief_fit_step_host": (c_i32, [c_vp, c_vp, C.POINTER(OptConfig), c_u64, c_i64, c_vp, c_vp]),
+    "brief_block_histogram": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp]),
     "brief_forward": (c_i32, [c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "brief_group_set_denorm": (c_i32, [c_vp, c_i32, c_f32, c_f32, c_f32, c_f32]),
     "brief_decompress": (c_i32, [c_vp, C.POINTER(c_vp), c_i32, c_vp]),

@@ -37,21 +37,40 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source into the one shared library. Returns its path."""
+    """Compile every CUDA source (one object per translation unit, in parallel, rebuilt only when the source or a
+    header is newer) and link the one shared library. Returns its path."""
     if not force and not _stale():
         return LIBPATH
-    os.makedirs(LIBDIR, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [_nvcc(), *flags, "-o", LIBPATH + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f not in ("--use_fast_math=false", "-shared")]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        flags += ["-Xptxas", "-v"]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + \
+              [os.path.join(os.path.dirname(HERE), "include", "brief_b200.h")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src[:-3] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), newest_header):
+            return obj, ""
+        res = subprocess.run([nvcc, *flags, "-c", "-o", obj, path], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), max(1, (os.cpu_count() or 2)))) as pool:
+        results = list(pool.map(compile_one, SOURCES))
     if verbose:
-        print(res.stdout, res.stderr)
+        for _, log in results:
+            print(log)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o",
+                          LIBPATH + ".tmp"] + [o for o, _ in results], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     os.replace(LIBPATH + ".tmp", LIBPATH)
     return LIBPATH
 

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -61,7 +62,7 @@ int tc_eval_tpb(long long total_tiles, int num_sms) {
   return (int)std::min<long long>(128, std::max<long long>(8, t));
 }
 constexpr int kBuckets = 9;  // F_PAD / 16 in 1..8
-constexpr int kWideStashSlots = 256;  // SM ids (%smid) the wide fit kernel's per-SM scratch covers; the kernel traps beyond
+constexpr int kHostStepSlots = 4;  // distinct (host index buffer, host loss buffer) pairs with a cached step graph
 
 template <class T>
 struct DevBuf {
@@ -91,9 +92,29 @@ struct WorkTable {  // block -> (network, local work index) for one kernel famil
 
 }  // namespace
 
+// One cached CUDA graph of a whole training step driven from HOST buffers (brief_fit_step_host):
+//   [H2D step scalars] -> [H2D sampler indices] -> fit kernel(s) -> optimiser kernel -> [D2H per-network loss]
+struct HostStepGraph {
+  const void* host_idx = nullptr;
+  float* host_loss = nullptr;
+  cudaStream_t stream = nullptr;
+  BriefOptConfig cfg{};
+  uint64_t seed = 0;
+  cudaGraphExec_t exec = nullptr;
+  cudaEvent_t done = nullptr;      // completion of the slot's last submission (its pinned scalars may be rewritten after it)
+  StepState* h_state = nullptr;    // pinned
+  StepState* d_state = nullptr;
+  long long* d_idx = nullptr;
+  float* d_loss = nullptr;
+  int kernels = 0;                 // kernel nodes per launch (gpu_launches accounting)
+};
+
 struct BriefGroup {
   int device = 0;
   int num_sms = 148;
+  int nsmid = 0;            // PTX %nsmid, queried when a wide tensor-core bucket first needs its per-SM scratch
+  HostStepGraph host_steps[kHostStepSlots];
+  int host_step_next = 0;
   int n_nets = 0;
   std::vector<NetDev> nets;
   long long total_P = 0, total_axis = 0;
@@ -118,7 +139,8 @@ struct BriefGroup {
   size_t simt_eval_smem = 0;
   WorkTable simt_eval, tc_eval[kBuckets];
   int tc_eval_tpb[kBuckets] = {0};  // decompress tiles per CTA, per bucket
-  int tc_L[kBuckets] = {0};  // deepest network per tensor-core bucket (sizes the dynamic shared memory)
+  int tc_L[kBuckets] = {0};      // deepest network per tensor-core bucket over ALL eval_tc networks (decompress launches)
+  int tc_fit_L[kBuckets] = {0};  // deepest network per bucket over the networks whose FIT runs on the tensor core
 };
 
 namespace {
@@ -197,6 +219,19 @@ struct TableBuilder {
   }
 };
 
+void drop_host_step_graph(HostStepGraph& h) {
+  if (h.exec) cudaGraphExecDestroy(h.exec);
+  if (h.done) cudaEventDestroy(h.done);
+  if (h.h_state) cudaFreeHost(h.h_state);
+  if (h.d_state) cudaFree(h.d_state);
+  if (h.d_idx) cudaFree(h.d_idx);
+  if (h.d_loss) cudaFree(h.d_loss);
+  h = HostStepGraph{};
+}
+void drop_host_step_graphs(BriefGroup* g) {
+  for (auto& h : g->host_steps) drop_host_step_graph(h);
+}
+
 // static decomposition of the dense-grid evaluation (decompress)
 int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   int tm = 128;
@@ -254,6 +289,10 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   }
   g->simt_fit_tm = tm;
   g->simt_fit_smem = 0;
+  drop_host_step_graphs(g);  // the captured launches carry the old decomposition
+  for (int b = 0; b < kBuckets; ++b) g->tc_fit_L[b] = 0;
+  for (auto& n : g->nets)
+    if (n.prec == BRIEF_PREC_F16) g->tc_fit_L[n.F_PAD / 16] = std::max(g->tc_fit_L[n.F_PAD / 16], n.L);
   // tensor-core networks: one CTA per slice; each width bucket is its own launch, so its slices are sized to fill
   // one wave of CTAs (SMs x resident CTAs of that bucket's kernel) by themselves
   long long tc_tiles[kBuckets] = {0}, tc_tps[kBuckets] = {0};
@@ -264,7 +303,7 @@ int finalize(BriefGroup* g, cudaStream_t st) {
     }
   for (int b = 1; b < kBuckets; ++b) {
     if (tc_tiles[b] == 0) continue;
-    const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(16 * b, g->tc_L[b]);
+    const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(16 * b, g->tc_fit_L[b]);
     tc_tps[b] = std::max<long long>(1, (tc_tiles[b] + wave - 1) / wave);
   }
   long long slice_total = 0, part_total = 0, idx_total = 0;
@@ -288,7 +327,7 @@ int finalize(BriefGroup* g, cudaStream_t st) {
     if (tc) {
       // PER_NETWORK: the network fills one wave by itself, so its slice boundaries (and with them the fp32
       // summation order of its gradients) do not depend on what else shares the GPU
-      const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(n.F_PAD, g->tc_L[n.F_PAD / 16]);
+      const long long wave = (long long)g->num_sms * tc_fit_ctas_per_sm(n.F_PAD, g->tc_fit_L[n.F_PAD / 16]);
       const long long own = g->slicing == BRIEF_SLICING_PER_NETWORK ? std::max<long long>(1, (n_tiles + wave - 1) / wave)
                                                                     : tc_tps[n.F_PAD / 16];
       tps = std::max<long long>(tps, own);
@@ -322,8 +361,14 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   size_t stash_total = 0;
   g->stash_stride = 0;
   for (int b = 5; b < kBuckets; ++b)
-    if (g->tc_fit[b].blocks > 0) g->stash_stride = std::max(g->stash_stride, tc_fit_stash_bytes(16 * b, g->tc_L[b]));
-  if (g->stash_stride > 0) stash_total = (size_t)kWideStashSlots * g->stash_stride;  // indexed by %smid, not by CTA
+    if (g->tc_fit[b].blocks > 0) g->stash_stride = std::max(g->stash_stride, tc_fit_stash_bytes(16 * b, g->tc_fit_L[b]));
+  if (g->stash_stride > 0) {
+    // indexed by %smid, whose range is [0, %nsmid): ask the device instead of assuming it equals the SM count
+    if (g->nsmid == 0) CU(query_nsmid(&g->nsmid, st));
+    if (g->nsmid < g->num_sms || g->nsmid > 4096)
+      return fail(BRIEF_ERR_UNSUPPORTED, "device reports %%nsmid = %d for %d SMs", g->nsmid, g->num_sms);
+    stash_total = (size_t)g->nsmid * g->stash_stride;
+  }
   if (stash_total > 0) CU(g->d_stash.ensure(stash_total));
   CU(g->d_loss_partials.ensure((size_t)slice_total));
   CU(g->d_loss_scratch.ensure((size_t)g->n_nets));
@@ -341,7 +386,8 @@ int ensure_wpack(BriefGroup* g, cudaStream_t st) {
   return 0;
 }
 
-int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st) {
+int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st,
+                       const StepState* state = nullptr) {
   FitArgs a{};
   a.nets = g->d_nets.p;
   a.params = g->d_params.p;
@@ -354,7 +400,8 @@ int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uin
   a.wpack = g->d_wpack.p;
   a.stash = g->d_stash.p;
   a.stash_stride = g->stash_stride;
-  a.stash_slots = kWideStashSlots;
+  a.stash_slots = g->nsmid;
+  a.state = state;
   if (g->simt_fit.blocks > 0) {
     a.work_prefix = g->d_fit_tables.p + g->simt_fit.off_prefix;
     a.work_net = g->d_fit_tables.p + g->simt_fit.off_net;
@@ -368,14 +415,34 @@ int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uin
     a.work_net = g->d_fit_tables.p + g->tc_fit[b].off_net;
     a.n_work = g->tc_fit[b].n;
     a.TM = kTcTile;
-    LAUNCH(launch_tc_fit(a, 16 * b, g->tc_L[b], g->tc_fit[b].blocks, st));
+    LAUNCH(launch_tc_fit(a, 16 * b, g->tc_fit_L[b], g->tc_fit[b].blocks, st));
   }
   return 0;
 }
 
+// learning rate of 1-based step t under MultiStepLR (utils/misc.py:187-188): scheduler.step() runs after
+// optimizer.step(), so step t uses lr0 * gamma^(#milestones <= t-1), accumulated by chained double multiplications
+double lr_at(const BriefOptConfig* cfg, int64_t t) {
+  double lr = cfg->lr;
+  for (int i = 0; i < cfg->n_milestones; ++i)
+    if (cfg->milestones[i] <= t - 1) lr *= (double)cfg->gamma;
+  return lr;
+}
+// torch: bias_correction = 1 - beta1 ** step ; clr = lr / bias_correction   (python doubles)
+void step_scalars(int kind, double lr, double b1, double b2, long long t, float* neg_clr, float* bc2_sqrt) {
+  if (kind == BRIEF_OPT_SGD) {
+    *neg_clr = (float)(-lr);
+    *bc2_sqrt = 1.f;
+  } else {
+    *neg_clr = (float)(-(lr / (1.0 - std::pow(b1, (double)t))));
+    *bc2_sqrt = (float)std::sqrt(1.0 - std::pow(b2, (double)t));
+  }
+}
+
 int launch_opt_kernel(BriefGroup* g, bool from_partials, bool apply, int kind, double lr, double b1, double b2,
-                      double eps, long long t, float* loss_out, cudaStream_t st) {
+                      double eps, long long t, float* loss_out, cudaStream_t st, const StepState* state = nullptr) {
   OptArgs o{};
+  o.state = state;
   o.nets = g->d_nets.p;
   o.blk_prefix = g->d_fit_tables.p + g->opt.off_prefix;
   o.n_nets = g->n_nets;
@@ -389,17 +456,12 @@ int launch_opt_kernel(BriefGroup* g, bool from_partials, bool apply, int kind, d
   o.kind = kind;
   o.apply = apply ? 1 : 0;
   if (apply) {
-    // torch: bias_correction = 1 - beta1 ** step ; clr = lr / bias_correction   (python doubles)
-    if (kind == BRIEF_OPT_SGD) {
-      o.neg_clr = (float)(-lr);
-    } else {
-      const double bc1 = 1.0 - std::pow(b1, (double)t);
-      o.neg_clr = (float)(-(lr / bc1));
+    step_scalars(kind, lr, b1, b2, t, &o.neg_clr, &o.bc2_sqrt);
+    if (kind != BRIEF_OPT_SGD) {
       o.w1 = (float)(1.0 - b1);
       o.beta2 = (float)b2;
       o.w2 = (float)(1.0 - b2);
       o.eps = (float)eps;
-      o.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(b2, (double)t));
     }
   }
   // the optimiser refreshes the fp16 operand image itself (image_scatter) — unless the image is already stale, in
@@ -554,6 +616,7 @@ int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device
 void brief_group_destroy(BriefGroup* g) {
   if (!g) return;
   cudaSetDevice(g->device);
+  drop_host_step_graphs(g);
   g->d_nets.release(); g->d_params.release(); g->d_grads.release(); g->d_m.release(); g->d_v.release();
   g->d_axes.release(); g->d_partials.release(); g->d_loss_partials.release(); g->d_loss_scratch.release();
   g->d_wpack.release(); g->d_stash.release(); g->d_fit_tables.release(); g->d_eval_tables.release(); g->d_outptrs.release();
@@ -738,16 +801,119 @@ int brief_fit_run(BriefGroup* g, const BriefOptConfig* cfg, uint64_t seed, int64
   RC(finalize(g, st));
   for (int64_t s = 0; s < n_steps; ++s) {
     const int64_t t = steps_done + s + 1;  // 1-based optimiser step
-    // MultiStepLR (utils/misc.py:187-188): scheduler.step() runs after optimizer.step(), so step t uses
-    // lr0 * gamma^(#milestones <= t-1), accumulated by chained double multiplications like torch.
-    double lr = cfg->lr;
-    for (int i = 0; i < cfg->n_milestones; ++i)
-      if (cfg->milestones[i] <= t - 1) lr *= (double)cfg->gamma;
+    const double lr = lr_at(cfg, t);
     RC(ensure_wpack(g, st));
     RC(launch_fit_kernels(g, nullptr, seed, (uint64_t)(t - 1), st));
     float* loss_out = dev_loss_hist ? dev_loss_hist + (size_t)s * g->n_nets : g->d_loss_scratch.p;
     RC(launch_opt_kernel(g, true, true, cfg->kind, lr, cfg->beta1, cfg->beta2, cfg->eps, t, loss_out, st));
   }
+  return 0;
+}
+
+// ---- one training step driven from HOST buffers, replayed as a CUDA graph --------------------------------------------
+static int enqueue_host_step(BriefGroup* g, HostStepGraph& h, long long n_idx, cudaStream_t st, int* kernels) {
+  const BriefOptConfig& c = h.cfg;
+  CU(cudaMemcpyAsync(h.d_state, h.h_state, sizeof(StepState), cudaMemcpyHostToDevice, st));
+  if (n_idx > 0) CU(cudaMemcpyAsync(h.d_idx, h.host_idx, (size_t)n_idx * sizeof(long long), cudaMemcpyHostToDevice, st));
+  const long long before = g_launches.load();
+  RC(launch_fit_kernels(g, n_idx > 0 ? reinterpret_cast<const int64_t*>(h.d_idx) : nullptr, h.seed, 0, st, h.d_state));
+  RC(launch_opt_kernel(g, true, true, c.kind, c.lr, c.beta1, c.beta2, c.eps, 1, h.d_loss, st, h.d_state));
+  *kernels = (int)(g_launches.load() - before);
+  if (h.host_loss) CU(cudaMemcpyAsync(h.host_loss, h.d_loss, sizeof(float) * g->n_nets, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int brief_fit_step_host(BriefGroup* g, const int64_t* host_idx, const BriefOptConfig* cfg, uint64_t seed, int64_t steps_done,
+                        float* host_loss, void* stream) {
+  if (!g || !cfg) return fail(BRIEF_ERR_INVALID, "null argument");
+  if (cfg->kind < 0 || cfg->kind > 2) return fail(BRIEF_ERR_INVALID, "unknown optimiser %d", cfg->kind);
+  if (cfg->n_milestones < 0 || cfg->n_milestones > 8) return fail(BRIEF_ERR_INVALID, "n_milestones=%d", cfg->n_milestones);
+  if (steps_done < 0) return fail(BRIEF_ERR_INVALID, "negative step count");
+  cudaStream_t st = (cudaStream_t)stream;
+  RC(use_device(g));
+  RC(check_bound(g));
+  RC(finalize(g, st));       // drops the cached graphs when the decomposition changed
+  RC(ensure_wpack(g, st));   // before capture: the captured optimiser launch then keeps the operand image current
+  long long n_idx = 0;
+  for (const auto& n : g->nets)
+    if (n.mode == BRIEF_SAMPLE_RANDOM_POINTS) n_idx += n.batch;
+  if (!host_idx) n_idx = 0;  // on-device sampler stream (Philox, keyed by seed and step)
+  // slot lookup: same buffers, stream and optimiser constants -> the cached graph is valid
+  HostStepGraph* h = nullptr;
+  for (auto& c : g->host_steps)
+    if (c.d_state && c.host_idx == host_idx && c.host_loss == host_loss && c.stream == st && c.seed == seed &&
+        memcmp(&c.cfg, cfg, sizeof(BriefOptConfig)) == 0) { h = &c; break; }
+  if (!h) {
+    h = &g->host_steps[g->host_step_next];
+    g->host_step_next = (g->host_step_next + 1) % kHostStepSlots;
+    if (h->done) cudaEventSynchronize(h->done);
+    drop_host_step_graph(*h);
+    h->host_idx = host_idx; h->host_loss = host_loss; h->stream = st; h->cfg = *cfg; h->seed = seed;
+    CU(cudaMallocHost(&h->h_state, sizeof(StepState)));
+    CU(cudaMalloc(&h->d_state, sizeof(StepState)));
+    CU(cudaMalloc(&h->d_loss, sizeof(float) * g->n_nets));
+    if (n_idx > 0) CU(cudaMalloc(&h->d_idx, (size_t)n_idx * sizeof(long long)));
+    CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
+    static const bool no_graph = getenv("BRIEF_NO_GRAPH") != nullptr;
+    if (!no_graph) {
+      // capture the same sequence a plain submission would enqueue (relaxed mode: the launchers call cudaFuncSetAttribute)
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+      if (e == cudaSuccess) {
+        int rc = enqueue_host_step(g, *h, n_idx, st, &h->kernels);
+        e = cudaStreamEndCapture(st, &graph);
+        if (rc != 0 || e != cudaSuccess || !graph) {
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          return rc ? rc : fail(BRIEF_ERR_CUDA, "capturing the step graph failed: %s", cudaGetErrorString(e));
+        }
+        g_launches.fetch_add(-(long long)h->kernels);  // captured, not launched
+        e = cudaGraphInstantiate(&h->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+      } else {
+        return fail(BRIEF_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  // this step's scalars: sampler stream position and the optimiser's step-dependent factors (host doubles like torch)
+  const int64_t t = steps_done + 1;
+  CU(cudaEventSynchronize(h->done));  // the slot's previous submission has consumed its pinned scalars
+  h->h_state->step = (unsigned long long)(t - 1);
+  step_scalars(cfg->kind, lr_at(cfg, t), cfg->beta1, cfg->beta2, t, &h->h_state->neg_clr, &h->h_state->bc2_sqrt);
+  if (h->exec) {
+    CU(cudaGraphLaunch(h->exec, st));
+    g_launches.fetch_add(h->kernels);
+  } else {
+    int k = 0;
+    RC(enqueue_host_step(g, *h, n_idx, st, &k));
+  }
+  CU(cudaEventRecord(h->done, st));
+  return 0;
+}
+
+int brief_block_histogram(const void* dev_raw, int64_t n, int32_t dtype, uint64_t* host_hist, int32_t device, void* stream) {
+  if (!dev_raw || !host_hist || n < 0) return fail(BRIEF_ERR_INVALID, "brief_block_histogram: bad arguments");
+  if (dtype != BRIEF_U8 && dtype != BRIEF_U16) return fail(BRIEF_ERR_UNSUPPORTED, "brief_block_histogram: uint8 / uint16 blocks only");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(BRIEF_ERR_CUDA, "CUDA device %d not available", device);
+  CU(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const size_t bins = dtype == BRIEF_U8 ? 256 : 65536;
+  unsigned long long* d = nullptr;
+  CU(cudaMalloc(&d, bins * sizeof(unsigned long long)));
+  cudaError_t e = cudaMemsetAsync(d, 0, bins * sizeof(unsigned long long), st);
+  if (e == cudaSuccess && n > 0) {
+    e = launch_histogram(dev_raw, n, dtype, d, sms, st);
+    if (e == cudaSuccess) g_launches.fetch_add(1);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host_hist, d, bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "brief_block_histogram: %s", cudaGetErrorString(e));
   return 0;
 }
 

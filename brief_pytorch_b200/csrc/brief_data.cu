@@ -178,4 +178,51 @@ cudaError_t launch_block_stats(const void* const* dev_ptrs, const long long* dev
 
 float stats_ord_to_float(unsigned int o) { return ord2f(o); }
 
+// ---- %nsmid: the wide fit kernel indexes its per-SM scratch by %smid, whose range is [0, %nsmid) — not the SM count ----
+__global__ void nsmid_kernel(unsigned int* out) {
+  unsigned int v;
+  asm volatile("mov.u32 %0, %%nsmid;" : "=r"(v));
+  *out = v;
+}
+cudaError_t query_nsmid(int* out, cudaStream_t st) {
+  unsigned int* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(unsigned int));
+  if (e != cudaSuccess) return e;
+  nsmid_kernel<<<1, 1, 0, st>>>(d);
+  unsigned int h = 0;
+  e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  *out = (int)h;
+  return e;
+}
+
+// ---- value histogram of a uint8 / uint16 block (quantile weight rules, utils/misc.py:298-305) -------------------------
+// hist[v] += number of voxels equal to v.  Biomedical volumes put most voxels into a handful of background values, so
+// equal values inside a warp are merged first (match.any) and one lane adds the whole count: a hot bin costs one
+// atomic per warp instead of 32.  Algorithmic bytes = the block, read once; not on the per-step path.
+template <typename T>
+__global__ void __launch_bounds__(256) hist_kernel(const T* __restrict__ p, long long n, unsigned long long* __restrict__ hist) {
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n; base += stride) {
+    const long long i = base + lane;
+    const bool ok = i < n;
+    const unsigned int v = ok ? (unsigned int)__ldg(p + i) : 0xffffffffu;
+    const unsigned int peers = __match_any_sync(0xffffffffu, v);
+    if (ok && lane == __ffs(peers) - 1) atomicAdd(hist + v, (unsigned long long)__popc(peers));
+  }
+}
+
+cudaError_t launch_histogram(const void* dev_raw, long long n, int dtype, unsigned long long* dev_hist, int num_sms,
+                             cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const long long want = (n + 255) / 256;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)num_sms * 16));
+  if (dtype == 0) hist_kernel<unsigned char><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(dev_raw), n, dev_hist);
+  else if (dtype == 1) hist_kernel<unsigned short><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned short*>(dev_raw), n, dev_hist);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 }  // namespace brief

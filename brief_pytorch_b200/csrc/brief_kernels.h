@@ -33,6 +33,14 @@ struct EvalArgs {
   int eval_slots;       // tile slots per group (2, or 1 for the widest networks)
 };
 
+// Per-step scalars that live in DEVICE memory when a step is replayed as a CUDA graph (brief_fit_step_host): the graph's
+// kernel arguments are frozen at capture time, so what changes from step to step is delivered by a memcpy node.
+struct StepState {
+  unsigned long long step;  // sampler stream position (Philox counter word)
+  float neg_clr;            // OptArgs::neg_clr of this step
+  float bc2_sqrt;           // OptArgs::bc2_sqrt of this step
+};
+
 // Fit work: block b serves slice (b - work_prefix[i]) of network work_net[i].
 struct FitArgs {
   const NetDev* nets;
@@ -49,7 +57,8 @@ struct FitArgs {
   const unsigned char* wpack;
   unsigned char* stash;     // wide tensor-core kernel: per-SM activation stash + dW scratch (stash_stride bytes per SM id)
   size_t stash_stride;
-  int stash_slots;          // SM ids covered by `stash`
+  int stash_slots;          // SM ids covered by `stash` (%nsmid of the device)
+  const StepState* state;   // non-NULL: `step` is read from device memory (graph replay)
 };
 
 // Optimiser step over the whole group (one launch).
@@ -73,6 +82,7 @@ struct OptArgs {
   float bc2_sqrt;    // sqrt(1 - beta2^t) (Adam)
   int apply;         // 0 = only reduce partials into grads / loss (brief_fit_step)
   unsigned char* wpack;  // refreshed fp16 operand image (tensor-core networks) or NULL
+  const StepState* state;  // non-NULL: neg_clr / bc2_sqrt are read from device memory (graph replay)
 };
 
 // brief_simt.cu
@@ -90,6 +100,9 @@ cudaError_t launch_sample_indices(uint64_t seed, uint64_t step, uint32_t net, lo
 cudaError_t launch_block_stats(const void* const* dev_ptrs, const long long* dev_sizes, int n_blocks, long long max_size,
                                int dtype, unsigned int* stat_ord, double* stat_sum, int num_sms, cudaStream_t st);
 float stats_ord_to_float(unsigned int o);
+cudaError_t query_nsmid(int* out, cudaStream_t st);  // PTX %nsmid: upper bound (exclusive) of %smid on this device
+cudaError_t launch_histogram(const void* dev_raw, long long n, int dtype, unsigned long long* dev_hist, int num_sms,
+                             cudaStream_t st);
 
 // brief_deblock.cu
 struct DeblockBlock { int z1, z2, y1, y2, x1, x2, mask; };  // inclusive ends; mask bit 0..3 = left, right, down, up seam listed

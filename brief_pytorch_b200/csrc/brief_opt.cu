@@ -113,9 +113,11 @@ __global__ void __launch_bounds__(kOptThreads) opt_kernel(OptArgs a) {
     g = a.grads[gi];
   }
   if (!a.apply) return;
+  const float neg_clr = a.state ? a.state->neg_clr : a.neg_clr;
+  const float bc2_sqrt = a.state ? a.state->bc2_sqrt : a.bc2_sqrt;
   float p = a.params[gi];
   if (a.kind == 2) {  // SGD: param.add_(grad, alpha=-lr)
-    p = fmaf(a.neg_clr, g, p);
+    p = fmaf(neg_clr, g, p);
   } else {
     float m = a.m[gi], v = a.v[gi];
     m = fmaf(a.w1, __fsub_rn(g, m), m);
@@ -125,9 +127,9 @@ __global__ void __launch_bounds__(kOptThreads) opt_kernel(OptArgs a) {
       den = v;
     } else {  // Adam
       v = __fadd_rn(__fmul_rn(v, a.beta2), __fmul_rn(__fmul_rn(a.w2, g), g));
-      den = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), a.bc2_sqrt), a.eps);
+      den = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), a.eps);
     }
-    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(a.neg_clr, m), den));
+    p = __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_clr, m), den));
     a.m[gi] = m;
     a.v[gi] = v;
   }

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kMaxThreads) simt_fit_kernel(FitArgs a) {
         long long idx;
         if (n.mode == 0) idx = s;
         else if (a.idx) idx = a.idx[n.idx_off + s];
-        else idx = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
+        else idx = brief_sample_index(a.seed, a.state ? a.state->step : a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
         brief_coords(n, a.axes, idx, c0, c1, c2);
         const float raw = brief_raw_value(n, idx);
         yv = brief_normalize(n, raw);

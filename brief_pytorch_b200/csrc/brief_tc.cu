@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         if (ok[h]) {
           if (n.mode == 0) v = s;
           else if (a.idx) v = a.idx[n.idx_off + s];
-          else v = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
+          else v = brief_sample_index(a.seed, a.state ? a.state->step : a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
         }
         idx[h] = v;
       }

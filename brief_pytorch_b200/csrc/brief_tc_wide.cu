@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
   // not grow with the grid and later CTAs of a multi-wave launch reuse lines that are already in L2
   unsigned int smid;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-  if (smid >= (unsigned int)a.stash_slots) __trap();
+  // smid < %nsmid == a.stash_slots: the host sizes the scratch from the device's own %nsmid (brief_capi.cu, finalize)
   unsigned char* stash = a.stash + (size_t)smid * a.stash_stride;  // a_j (j <= NH-2) at stash + j * BUF
   float4* scr = reinterpret_cast<float4*>(stash + (size_t)(NH >= 2 ? NH - 1 : 0) * BUF);  // running dW sums, see below
 
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
     if (ok) {
       if (n.mode == 0) v = s;
       else if (a.idx) v = a.idx[n.idx_off + s];
-      else v = brief_sample_index(a.seed, a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
+      else v = brief_sample_index(a.seed, a.state ? a.state->step : a.step, n.stream_id, (uint64_t)s, (uint64_t)n.n_vox);
     }
     const float raw = brief_raw_value(n, v);
     float x0, x1, x2;

@@ -17,7 +17,7 @@ from . import _cabi
 from ._cabi import (DT_F32, DT_U16, DT_U8, OPT_ADAM, OPT_ADAMAX, OPT_SGD, PREC_AUTO, PREC_F16, PREC_FP32,
                     SAMPLE_FULL_BLOCK, SAMPLE_RANDOM_POINTS, check)
 
-_PREC = {"fp32": PREC_FP32, "f16": PREC_F16, "bf16": PREC_F16, "auto": PREC_AUTO}  # "bf16": alias of the tensor-core mode
+_PREC = {"fp32": PREC_FP32, "f16": PREC_F16, "auto": PREC_AUTO}  # "f16": tcgen05 kind::f16 with fp16 operands
 _OPT = {"Adamax": OPT_ADAMAX, "Adam": OPT_ADAM, "SGD": OPT_SGD}
 _NP2DT = {"uint8": DT_U8, "uint16": DT_U16, "float32": DT_F32}
 _DT2TORCH = {DT_U8: torch.uint8, DT_U16: torch.int16, DT_F32: torch.float32}  # u16 held as int16 bit patterns
@@ -236,6 +236,27 @@ class SirenGroup:
         self.steps_done += n_steps
         return hist
 
+    def fit_step_host(self, host_idx: Optional[torch.Tensor], host_loss: Optional[torch.Tensor], kind: str = "Adamax",
+                      lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, milestones: Sequence[int] = (),
+                      gamma: float = 0.2, seed: int = 42) -> None:
+        """One whole step (main.py:385-401) from HOST buffers as one CUDA-graph launch: pinned int64 sampler indices
+        (all RANDOM_POINTS networks concatenated; None = on-device sampler) -> device, fit, optimiser, per-network loss
+        -> pinned `host_loss`.  Asynchronous: synchronise the current stream (or an event recorded on it) before reading
+        `host_loss` or refilling `host_idx`; alternate two buffer sets to keep the GPU busy."""
+        for t in (host_idx, host_loss):
+            if t is not None:
+                assert (not t.is_cuda) and t.is_pinned() and t.is_contiguous()
+        if host_idx is not None:
+            assert host_idx.dtype == torch.int64
+        if host_loss is not None:
+            assert host_loss.dtype == torch.float32 and host_loss.numel() >= len(self.specs)
+        cfg = _cabi.OptConfig(_OPT[kind], lr, betas[0], betas[1], eps, len(milestones),
+                              (C.c_int64 * 8)(*list(milestones)[:8]), gamma)
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_fit_step_host(self._h, _ptr(host_idx), C.byref(cfg), seed, self.steps_done,
+                                                _ptr(host_loss), _stream(self.device)))
+        self.steps_done += 1
+
     def forward(self, net: int, coords: torch.Tensor, return_layers: bool = False):
         """SIREN.forward on explicit coordinates [..., coords_channel] -> [..., 1] (fp32, CUDA)."""
         s = self.specs[net]
@@ -332,6 +353,20 @@ def block_stats(blocks: Sequence[torch.Tensor], np_dtype: Optional[str] = None) 
         check(lib.brief_block_stats(ptrs, sizes, n, _NP2DT[np_dtype], dev.index if dev.index is not None else 0,
                                     out.ctypes.data_as(C.POINTER(C.c_double)), _stream(dev)))
     return out
+
+
+def block_histogram(block: torch.Tensor, np_dtype: Optional[str] = None) -> np.ndarray:
+    """Value histogram (int64 [256] / [65536]) of a raw uint8 / uint16 CUDA block (uint16 as int16 bit patterns) in one
+    launch — the device half of the 'quantile' weight rule (utils/misc.py:298-305)."""
+    lib = _cabi.load()
+    assert block.is_cuda and block.is_contiguous()
+    if np_dtype is None:
+        np_dtype = {torch.uint8: "uint8", torch.int16: "uint16"}[block.dtype]
+    out = np.zeros(256 if np_dtype == "uint8" else 65536, dtype=np.uint64)
+    with torch.cuda.device(block.device):
+        check(lib.brief_block_histogram(_ptr(block), block.numel(), _NP2DT[np_dtype], out.ctypes.data_as(C.c_void_p),
+                                        block.device.index or 0, _stream(block.device)))
+    return out.astype(np.int64)
 
 
 def volume_quality(a: torch.Tensor, b: torch.Tensor, data_range: float, np_dtype: Optional[str] = None) -> dict:

@@ -79,23 +79,73 @@ def preprocess(data: np.ndarray, denoise_level, denoise_close, clip_range, devic
     return (out.view(np.uint16) if data.dtype == np.uint16 else out)[..., None]
 
 
-def weight_rules_for_kernel(data: np.ndarray, weight_type_list: Iterable[str]):
+def quantile_from_histogram(hist: np.ndarray, ge_thres: float, q: float) -> float:
+    """np.quantile(data[data >= ge_thres], q) (default 'linear' method) for integer-valued data given only its
+    histogram `hist[v] = #voxels == v`: the two neighbouring order statistics are read off the cumulative counts and
+    interpolated with numpy's own lerp formula, so the result is the float64 numpy returns."""
+    hist = np.asarray(hist, dtype=np.int64)
+    first = int(np.ceil(max(ge_thres, 0.0)))
+    counts = hist.copy()
+    counts[:min(first, counts.size)] = 0
+    n = int(counts.sum())
+    if n == 0:
+        return float("nan")  # numpy: quantile of an empty selection
+    cum = np.cumsum(counts)
+    vidx = (n - 1) * np.float64(q)
+    prev = int(np.floor(vidx))
+    gamma = vidx - prev
+    nxt = min(prev + 1, n - 1)
+    a = np.float64(np.searchsorted(cum, prev + 1, side="left"))   # value of the order statistic with 0-based rank prev
+    b = np.float64(np.searchsorted(cum, nxt + 1, side="left"))
+    diff = b - a
+    return float(b - diff * (1 - gamma)) if gamma >= 0.5 else float(a + diff * gamma)
+
+
+def weight_rules_for_kernel(data, weight_type_list: Iterable[str], np_dtype=None):
     """Translate rule strings into on-chip (lo, hi, scale) triples; returns None when a rule needs the
-    explicit weight volume ('exp', or more than 4 rules)."""
+    explicit weight volume ('exp', or more than 4 rules).  `data`: the raw block as a numpy array or as a CUDA tensor
+    (uint16 as int16 bit patterns, with `np_dtype`); only a 'quantile' rule looks at the voxels — through a device
+    histogram (brief_block_histogram) when the block is a CUDA tensor of uint8 / uint16."""
+    dt = np.dtype(np_dtype) if np_dtype is not None else np.asarray(data).dtype
+    probe = np.zeros(0, dt)
     rules = []
+    hist = None
     for rule in weight_type_list:
         if rule == "none":
             continue
         kind, *args = rule.split("_")
         vals = [float(a) for a in args]
         if kind == "value":
-            rules.append(_limits(data, vals[0], vals[1]) + (vals[2],))
+            rules.append(_limits(probe, vals[0], vals[1]) + (vals[2],))
         elif kind == "quantile":
-            sel = data[data >= vals[0]]
-            rules.append(_limits(data, float(np.quantile(sel, vals[1])), float(np.quantile(sel, vals[2]))) + (vals[3],))
+            if isinstance(data, torch.Tensor) and data.is_cuda and dt in (np.uint8, np.uint16):
+                if hist is None:
+                    from .group import block_histogram
+                    hist = block_histogram(data, dt.name)
+                ql, qh = quantile_from_histogram(hist, vals[0], vals[1]), quantile_from_histogram(hist, vals[0], vals[2])
+            else:
+                host = data.cpu().numpy() if isinstance(data, torch.Tensor) else np.asarray(data)
+                host = host.view(np.uint16) if (dt == np.uint16 and host.dtype == np.int16) else host
+                sel = host[host >= vals[0]]
+                ql, qh = float(np.quantile(sel, vals[1])), float(np.quantile(sel, vals[2]))
+            rules.append(_limits(probe, ql, qh) + (vals[3],))
         else:
             return None
     return rules if len(rules) <= 4 else None
+
+
+def check_float_preprocess_is_identity(blocks, pre) -> None:
+    """brief_preprocess handles uint8 / uint16 volumes.  For float32 blocks the configured preprocess is accepted only
+    when it provably changes nothing (no voxel at or below the level, clip range covering the data); anything else is
+    refused loudly instead of being skipped."""
+    level, (lo, hi) = pre["denoise"]["level"], pre["clip"]
+    for b in blocks:
+        arr = b.data if b.data is not None else None
+        vmin = float(arr.min()) if arr is not None else float(b.dev.min())
+        vmax = float(arr.max()) if arr is not None else float(b.dev.max())
+        if vmin <= level or vmin < lo or vmax > hi:
+            raise NotImplementedError("Compress.preprocess on float32 data that the threshold / clip would change: "
+                                      "brief_preprocess covers uint8 / uint16 volumes")
 
 
 # ---- optimiser / schedule configuration -------------------------------------------------------------------
@@ -212,10 +262,39 @@ def divide_data(data: np.ndarray, divide_type: str):
     return chunks, None
 
 
+def variance_from_sums(s1: float, s2: float, n: int) -> float:
+    """Population variance of a block from its exact integer sums (brief_block_stats): E[x^2] - mean^2 in float64.
+    The reference's two-pass ((x - mean)^2).mean() agrees to ~1e-14 relative; budgets are not a bit-exact quantity."""
+    m = s1 / n
+    return float(s2 / n - m * m)
+
+
+def cal_feature(image: np.ndarray) -> float:
+    """utils/adaptive_blocking.py:16-24 for a [d,h,w,c] block: max / sum of the 3-D FFT magnitudes (the DC share of
+    the spectrum), with the reference's int() truncations.  Host numpy like the reference: it runs once per block
+    before the fit and numpy's FFT is what makes the budgets bit-identical."""
+    if image.ndim != 4:
+        raise NotImplementedError("cal_feature: [d,h,w,c] blocks")
+    f = np.abs(np.fft.fft(np.fft.fft(np.fft.fft(image, axis=0), axis=1), axis=2))
+    return int(f.max()) / int(f.sum())
+
+
 def alloc_param(data_chunk_list: List[dict], param_size: float, param_alloc: str, param_size_thres: float):
-    """Split the byte budget over blocks (equal | by_size | by_var) and drop blocks below the threshold,
-    re-allocating until stable (utils/misc.py:395-428)."""
+    """Split the byte budget over blocks (equal | by_size | by_var | by_d | by_dv) and drop blocks below the
+    threshold, re-allocating until stable (utils/misc.py:395-428).  A chunk may carry a precomputed 'var' (from the
+    device statistics kernel) or 'feature'; otherwise they are computed from chunk['data'] like the reference."""
     chunks = list(data_chunk_list)
+
+    def var_of(c):
+        if "var" not in c:
+            c["var"] = ((c["data"] - c["data"].mean()) ** 2).mean()
+        return c["var"]
+
+    def feat_of(c):
+        if "feature" not in c:
+            c["feature"] = cal_feature(c["data"])
+        return c["feature"]
+
     while True:
         if param_alloc == "equal":
             for c in chunks:
@@ -224,14 +303,25 @@ def alloc_param(data_chunk_list: List[dict], param_size: float, param_alloc: str
             for c in chunks:
                 c["param_size"] = param_size * c["size"] / c["total_size"]
         elif param_alloc == "by_var":
-            var = [((c["data"] - c["data"].mean()) ** 2).mean() for c in chunks]
             total = 0
-            for v in var:
-                total += v
-            for c, v in zip(chunks, var):
-                c["param_size"] = float(param_size * v / total)
+            for c in chunks:
+                total += var_of(c)
+            for c in chunks:
+                c["param_size"] = float(param_size * var_of(c) / total)
+        elif param_alloc == "by_d":
+            total = 0
+            for c in chunks:
+                total += 1 / feat_of(c)
+            for c in chunks:
+                c["param_size"] = float(param_size * (1 / feat_of(c)) / total)
+        elif param_alloc == "by_dv":
+            total = 0
+            for c in chunks:
+                total += c["size"] / feat_of(c)
+            for c in chunks:
+                c["param_size"] = float(param_size * (c["size"] / feat_of(c)) / total)
         else:
-            raise NotImplementedError(f"param_alloc '{param_alloc}' needs the FFT block feature (not on the hot path)")
+            raise NotImplementedError(param_alloc)
         kept = [c for c in chunks if c["param_size"] >= param_size_thres]
         if len(kept) == len(chunks):
             return kept

@@ -77,40 +77,51 @@ def gather_block_stats(local: torch.Tensor, owner: Sequence[int], group=None) ->
 
 
 def gather_blocks(local: Dict[int, torch.Tensor], owner: Sequence[int], shapes: Sequence[Sequence[int]], dst: int = 0,
-                  group=None) -> Optional[Dict[int, torch.Tensor]]:
-    """Send every decompressed block (any integer / float dtype, all blocks the same dtype) to rank `dst`.
-    Point-to-point per block, variable sizes; returns {block id: tensor} on dst and None elsewhere.  For outputs
-    that do not fit one GPU (the 4096^3 sweep) do not call this: keep the volume sharded by owner."""
+                  group=None, dtype: Optional[torch.dtype] = None) -> Optional[Dict[int, torch.Tensor]]:
+    """Bring every decompressed block to rank `dst` (merge_divided_data's input, utils/misc.py:430-445).  Every rank
+    packs its blocks into ONE contiguous payload (a device copy at HBM rate) and the exchange is a single grouped
+    send/recv — one message per sending rank instead of one per block and no pickled metadata: sizes follow from
+    `owner`, `shapes` and `dtype` (inferred from the local blocks; pass it on a rank that owns none).  On `dst` the
+    blocks are views into the per-sender receive buffers.  Returns {block id: tensor} on dst and None elsewhere.  For
+    outputs that do not fit one GPU (the 4096^3 sweep) do not call this: keep the volume sharded by owner."""
     rank, world = _world()
     if world == 1:
         return dict(local)
-    out: Dict[int, torch.Tensor] = {}
-    ops, keep = [], []
+    if dtype is None:
+        if not local:
+            raise ValueError("gather_blocks: pass dtype= on a rank that owns no block")
+        dtype = next(iter(local.values())).dtype
+    esz = int(torch.empty((), dtype=dtype).element_size())
+    nbytes = []
+    for sh in shapes:
+        n = esz
+        for x in sh:
+            n *= int(x)
+        nbytes.append(n)
+    by_rank = [[b for b, r in enumerate(owner) if r == q] for q in range(world)]
     ref = next(iter(local.values())) if local else None
-    meta = [None] * world
-    dist.all_gather_object(meta, None if ref is None else (str(ref.dtype), str(ref.device.type)), group=group)
-    dtype_name = next(m[0] for m in meta if m is not None)
-    dtype = getattr(torch, dtype_name.split(".")[-1])
-    for b, r in enumerate(owner):
-        if r == dst:
-            if rank == dst:
-                out[b] = local[b]
-            continue
-        # payloads travel as raw bytes: NCCL has no 16-bit integer type (uint16 volumes are held as int16 bit patterns)
-        if rank == r:
-            t = local[b].contiguous().view(torch.uint8)
-            keep.append(t)
-            ops.append(dist.P2POp(dist.isend, t, dst, group=group))
-        elif rank == dst:
-            dev = ref.device if ref is not None else ("cuda" if torch.cuda.is_available() else "cpu")
-            shape = tuple(int(x) for x in shapes[b])
-            n_bytes = int(torch.empty((), dtype=dtype).element_size())
-            for x in shape:
-                n_bytes *= x
-            t = torch.empty(n_bytes, dtype=torch.uint8, device=dev)
-            out[b] = t.view(dtype).reshape(shape)
-            ops.append(dist.P2POp(dist.irecv, t, r, group=group))
+    dev = ref.device if ref is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    ops, keep, bufs = [], [], {}
+    # payloads travel as raw bytes: NCCL has no 16-bit integer type (uint16 volumes are held as int16 bit patterns)
+    if rank == dst:
+        for q in range(world):
+            if q != dst and by_rank[q]:
+                bufs[q] = torch.empty(sum(nbytes[b] for b in by_rank[q]), dtype=torch.uint8, device=dev)
+                ops.append(dist.P2POp(dist.irecv, bufs[q], q, group=group))
+    elif by_rank[rank]:
+        parts = [local[b].contiguous().view(torch.uint8).reshape(-1) for b in by_rank[rank]]
+        payload = parts[0] if len(parts) == 1 else torch.cat(parts)
+        keep.append(payload)
+        ops.append(dist.P2POp(dist.isend, payload, dst, group=group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-    return out if rank == dst else None
+    if rank != dst:
+        return None
+    out: Dict[int, torch.Tensor] = {b: local[b] for b in by_rank[dst]}
+    for q, buf in bufs.items():
+        off = 0
+        for b in by_rank[q]:
+            out[b] = buf[off:off + nbytes[b]].view(dtype).reshape(tuple(int(x) for x in shapes[b]))
+            off += nbytes[b]
+    return out

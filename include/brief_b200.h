@@ -175,6 +175,18 @@ int brief_opt_step(BriefGroup* g, int32_t kind, float lr, float beta1, float bet
 int brief_fit_run(BriefGroup* g, const BriefOptConfig* cfg, uint64_t seed, int64_t steps_done, int64_t n_steps,
                   float* dev_loss_hist, void* stream);
 
+/* The loop body of main.py:385-401 for ONE step with HOST buffers — what a caller that draws the sampler indices with
+ * the CPU generator (main.py:156) and reads loss.item() every step (main.py:401) needs — enqueued on `stream` as ONE
+ * CUDA-graph launch: [host->device: step scalars, sampler indices] -> fit kernel(s) -> optimiser kernel ->
+ * [device->host: per-network loss].  host_idx: PINNED host memory, int64, all RANDOM_POINTS networks' indices
+ * concatenated in network order (NULL: on-device sampler stream keyed by seed and step); host_loss: PINNED host
+ * memory, n_nets floats, or NULL.  `steps_done` completed steps precede this one (optimiser step count, MultiStepLR
+ * position, sampler stream position).  The call returns as soon as the step is enqueued; the caller synchronises on
+ * `stream` before it reads host_loss or rewrites host_idx.  The graph is built on the first call for a given
+ * (host_idx, host_loss, stream, cfg) and replayed afterwards; up to 4 such buffer sets are cached (double buffering). */
+int brief_fit_step_host(BriefGroup* g, const int64_t* host_idx, const BriefOptConfig* cfg, uint64_t seed,
+                        int64_t steps_done, float* host_loss, void* stream);
+
 /* SIREN.forward on caller coordinates (utils/Networks.py:269-271): dev_coords [n][coords_channel] fp32
  * -> dev_out [n][1] fp32.  dev_layers (optional, may be NULL): pre-activations z_l of every layer,
  * layout [layers-1][n][features] fp32, for per-layer parity checks. */
@@ -207,6 +219,11 @@ int brief_sample_indices(uint64_t seed, uint64_t step, int32_t net, int64_t batc
  * (accumulated in fp64).  Synchronises `stream`. */
 int brief_block_stats(void* const* host_dev_raw, const int64_t* host_sizes, int32_t n_blocks, int32_t dtype,
                       int32_t device, double* host_out, void* stream);
+
+/* Value histogram of one raw uint8 / uint16 block in device memory (host_hist: 256 / 65536 counters): what the
+ * 'quantile_ge_ql_qh_s' weight rule needs instead of np.quantile over a host copy of the block (utils/misc.py:298-305;
+ * the two order statistics are read off the cumulative counts).  Synchronises `stream`. */
+int brief_block_histogram(const void* dev_raw, int64_t n, int32_t dtype, uint64_t* host_hist, int32_t device, void* stream);
 
 /* Replaces the reference's `preprocess` (utils/misc.py:244-254; called on every block before the fit, main.py:336,
  * and on every decoded block, main.py:295) on one block [depth][height][width] of uint8 / uint16 voxels in device

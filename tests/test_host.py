@@ -157,3 +157,57 @@ def test_optimizer_config_mirror():
     assert abs(opt.lr_at(50001) - 2e-4) < 1e-12 and abs(opt.lr_at(70001) - 8e-6) < 1e-12
     with pytest.raises(NotImplementedError):
         misc.configure_optimizer(None, "RMSprop", 1e-3)
+
+
+def test_alloc_param_by_d_by_dv_match_reference():
+    """utils/misc.py:410-422 + utils/adaptive_blocking.py:16-24: golden vectors from the unmodified reference
+    (oracle/gen_golden_alloc.py); numpy's FFT on the host like the reference, so the budgets are bit-identical."""
+    g = load_gold("alloc_d")
+    for tag in ("small", "hipct"):
+        vol = g[f"{tag}_volume"]
+        for dt in ("total_2_2_2", "every_7_9_11"):
+            chunks, _ = misc.divide_data(vol.copy(), dt)
+            np.testing.assert_array_equal([misc.cal_feature(c["data"]) for c in chunks], g[f"{tag}_{dt}_feature"])
+            for alloc in ("by_d", "by_dv"):
+                kept = misc.alloc_param([dict(c) for c in chunks], 9000.0, alloc, 26)
+                assert [c["name"] for c in kept] == list(g[f"{tag}_{dt}_{alloc}_names"])
+                np.testing.assert_array_equal([float(c["param_size"]) for c in kept], g[f"{tag}_{dt}_{alloc}_sizes"])
+
+
+def test_alloc_param_by_var_from_block_sums():
+    """The device statistics kernel returns exact integer sums; the variance formed from them gives the reference's
+    by_var budgets to ~1e-12 relative and the same widths."""
+    g = load_gold("partition")
+    vol = g["volume"]
+    chunks, _ = misc.divide_data(vol.copy(), "total_2_2_3")
+    want = g["total_2_2_3_by_var_sizes"]
+    for c in chunks:
+        x = c["data"].astype(np.int64)
+        c["var"] = misc.variance_from_sums(float(x.sum()), float((x * x).sum()), c["size"])
+    kept = misc.alloc_param(chunks, 9000.0, "by_var", 26)
+    np.testing.assert_allclose([c["param_size"] for c in kept], want, rtol=1e-12)
+
+
+def test_quantile_from_histogram_is_numpy_quantile():
+    rng = np.random.default_rng(7)
+    for dtype, hi in ((np.uint16, 65536), (np.uint8, 256)):
+        for trial in range(6):
+            n = int(rng.integers(1, 5000))
+            data = (rng.gamma(2.0, hi / 40, n).clip(0, hi - 1)).astype(dtype)
+            hist = np.bincount(data.ravel(), minlength=hi)
+            for ge in (0.0, float(np.median(data)), 3.5):
+                sel = data[data >= ge]
+                if sel.size == 0:
+                    continue
+                for q in (0.0, 0.1, 0.37, 0.5, 0.9, 0.999, 1.0):
+                    assert misc.quantile_from_histogram(hist, ge, q) == float(np.quantile(sel, q)), (dtype, n, ge, q)
+    # the kernel-rule translation with a host array goes through np.quantile itself
+    data = (rng.gamma(2.0, 2000, (6, 7, 8, 1)).clip(0, 65535)).astype(np.uint16)
+    rules = misc.weight_rules_for_kernel(data, ["quantile_100_0.2_0.8_0.5", "value_0_50_2"])
+    sel = data[data >= 100]
+    assert rules == [(float(np.quantile(sel, 0.2)), float(np.quantile(sel, 0.8)), 0.5), (0.0, 50.0, 2.0)]
+    w = misc.parse_weight(data, ["quantile_100_0.2_0.8_0.5", "value_0_50_2"])
+    ref_w = np.ones(data.shape, np.float32)
+    ref_w[(data >= rules[0][0]) & (data <= rules[0][1])] = 0.5
+    ref_w[(data >= 0) & (data <= 50)] = 2
+    np.testing.assert_array_equal(w, ref_w)

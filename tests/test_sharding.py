@@ -74,3 +74,64 @@ def test_gathers_world_size_2_gloo():
     assert sorted(blocks) == list(range(5))
     for b, arr in blocks.items():
         assert arr.shape == (2, 3, b + 1) and (arr == 1000 + b).all()
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import zlib
+        import yaml
+        from brief_pytorch_b200 import synth
+        from brief_pytorch_b200.CompressFramework import NFGR
+        from brief_pytorch_b200.group import pack_module_params
+        from test_framework import VESSEL_YAML
+        o = yaml.safe_load(VESSEL_YAML)
+        o["Compress"]["divide"]["divide_type"] = "total_1_2_4"
+        o["Compress"]["param"]["filesize_ratio"] = 16
+        o["Compress"]["checkpoints"] = "none"
+        vol = synth.vessel((16, 48, 96), seed=7)
+        blocks, mine = NFGR(o, rank, "f16", reproducible=True).compress_divide(vol, None, max_steps=12, rank=rank, world=world)
+        owner = [0] * len(blocks)
+        for i in mine:
+            owner[i] = rank
+        own = torch.tensor([float(i in mine) for i in range(len(blocks))], device="cuda")
+        dist.all_reduce(own)
+        assert (own == 1).all()  # every block fitted by exactly one rank
+        crc = torch.tensor([[float(zlib.crc32(pack_module_params(blocks[i].module).tobytes()))] for i in mine],
+                           dtype=torch.float64, device="cuda").reshape(-1, 1)
+        who = torch.zeros(len(blocks), device="cuda")
+        for i in mine:
+            who[i] = rank
+        dist.all_reduce(who)
+        table = sharding.gather_block_stats(crc, [int(x) for x in who.tolist()])
+        single = None
+        if rank == 0:
+            ref_blocks, _ = NFGR(o, 0, "f16", reproducible=True).compress_divide(vol, None, max_steps=12)
+            single = [float(zlib.crc32(pack_module_params(b.module).tobytes())) for b in ref_blocks]
+        q.put((rank, table[:, 0].cpu().tolist(), single))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpu_sharding_gives_bit_identical_blocks_nccl():
+    """SURVEY 8(e) on hardware: the same volume fitted by 2 ranks (one process per GPU, NCCL) and by 1 rank gives
+    bit-identical parameters for every block (reproducible slicing; the only collectives are the stats gathers)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        rank, table, single = q.get(timeout=600)
+        res[rank] = (table, single)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res[0][0] == res[1][0] == res[0][1]
