@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIBPATH = os.path.join(LIBDIR, "libbrief_b200.so")
-SOURCES = ["brief_capi.cu", "brief_simt.cu", "brief_opt.cu", "brief_tc.cu", "brief_tc_wide.cu", "brief_data.cu", "brief_deblock.cu", "brief_quality.cu",
+SOURCES = ["brief_capi.cu", "brief_simt.cu", "brief_opt.cu", "brief_tc.cu", "brief_tc_wide.cu", "brief_tc_lw.cu", "brief_data.cu", "brief_deblock.cu", "brief_quality.cu",
            "brief_preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -109,12 +109,25 @@ struct HostStepGraph {
   int kernels = 0;                 // kernel nodes per launch (gpu_launches accounting)
 };
 
+// One pass of the layer-wise path: networks `nets` (all of padded width F and depth L) whose tiles share the scratch arena.
+struct LwPass {
+  int F = 0, L = 0;
+  long long T = 0;            // tiles of the pass
+  std::vector<int> nets, tile_count, tile_first, tile_prefix, cta_prefix;
+  std::vector<long long> tile_base;
+  int off = 0, off_base = 0;  // offsets of this pass's tables in the device table buffers
+  int max_slices = 1;
+  int ctas() const { return cta_prefix.empty() ? 0 : cta_prefix.back(); }
+};
+
 struct BriefGroup {
   int device = 0;
   int num_sms = 148;
   int nsmid = 0;            // PTX %nsmid, queried when a wide tensor-core bucket first needs its per-SM scratch
   HostStepGraph host_steps[kHostStepSlots];
   int host_step_next = 0;
+  cudaStream_t capture_stream = nullptr;  // step graphs are captured here (the caller's stream may be the legacy default
+                                          // stream, which cannot be captured) and launched into the caller's stream
   int n_nets = 0;
   std::vector<NetDev> nets;
   long long total_P = 0, total_axis = 0;
@@ -141,11 +154,69 @@ struct BriefGroup {
   int tc_eval_tpb[kBuckets] = {0};  // decompress tiles per CTA, per bucket
   int tc_L[kBuckets] = {0};      // deepest network per tensor-core bucket over ALL eval_tc networks (decompress launches)
   int tc_fit_L[kBuckets] = {0};  // deepest network per bucket over the networks whose FIT runs on the tensor core
+  // layer-wise tensor-core path (128 < F_PAD <= 256, brief_tc_lw.cu): passes of networks of one (F_PAD, L)
+  std::vector<LwPass> lw_fit, lw_eval;
+  DevBuf<int> d_lw_fit_tab, d_lw_eval_tab;
+  DevBuf<long long> d_lw_fit_base, d_lw_eval_base;
+  DevBuf<unsigned char> d_lw_scratch;
 };
 
 namespace {
 
 int f4_of(int f) { return (f + 3) & ~3; }
+inline bool is_lw(const NetDev& n) { return n.eval_tc && n.F_PAD > 128; }  // layer-wise tensor-core path (brief_tc_lw.cu)
+constexpr size_t kLwScratchBudget = (size_t)6 << 30;  // scratch arena of one layer-wise pass
+
+// Device tables of a set of passes: per pass [tile_prefix (n+1) | cta_prefix (n+1) | work_net (n) | tile_count (n) | tile_first (n)]
+int upload_lw_tables(std::vector<LwPass>& passes, DevBuf<int>& tab, DevBuf<long long>& base, int num_sms, cudaStream_t st) {
+  std::vector<int> t;
+  std::vector<long long> b;
+  for (auto& p : passes) {
+    const int n = (int)p.nets.size();
+    p.tile_prefix.assign(1, 0);
+    p.cta_prefix.assign(1, 0);
+    p.tile_base.clear();
+    long long T = 0;
+    for (int i = 0; i < n; ++i) {
+      p.tile_base.push_back(T);
+      T += p.tile_count[i];
+      p.tile_prefix.push_back((int)T);
+    }
+    p.T = T;
+    for (int i = 0; i < n; ++i) {  // GEMM CTAs in proportion to the tiles, at least one per network
+      long long c = (long long)num_sms * p.tile_count[i] / std::max<long long>(T, 1);
+      c = std::max<long long>(1, std::min<long long>(c, p.tile_count[i]));
+      p.cta_prefix.push_back(p.cta_prefix.back() + (int)c);
+    }
+    p.off = (int)t.size();
+    t.insert(t.end(), p.tile_prefix.begin(), p.tile_prefix.end());
+    t.insert(t.end(), p.cta_prefix.begin(), p.cta_prefix.end());
+    t.insert(t.end(), p.nets.begin(), p.nets.end());
+    t.insert(t.end(), p.tile_count.begin(), p.tile_count.end());
+    t.insert(t.end(), p.tile_first.begin(), p.tile_first.end());
+    p.off_base = (int)b.size();
+    b.insert(b.end(), p.tile_base.begin(), p.tile_base.end());
+  }
+  CU(tab.ensure(t.size()));
+  CU(base.ensure(b.size()));
+  if (!t.empty()) CU(cudaMemcpyAsync(tab.p, t.data(), t.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!b.empty()) CU(cudaMemcpyAsync(base.p, b.data(), b.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+void lw_bind_tables(LwArgs& a, const LwPass& p, const int* tab, const long long* base, bool ctas) {
+  const int n = (int)p.nets.size();
+  const int* t = tab + p.off;
+  a.work_prefix = ctas ? t + (n + 1) : t;
+  a.work_net = t + 2 * (n + 1);
+  a.tile_count = t + 2 * (n + 1) + n;
+  a.tile_first = t + 2 * (n + 1) + 2 * n;
+  a.tile_base = base + p.off_base;
+  a.n_work = n;
+  a.F = p.F;
+  a.T = p.T;
+  a.max_slices = p.max_slices;
+}
 
 // reference packed order (utils/ModelSave.py:32-51) <-> padded device layout ----------------------
 void packed_to_dev(const NetDev& n, const float* src, float* dst) {
@@ -248,10 +319,11 @@ int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
   long long bucket_tiles[kBuckets] = {0};
   for (const auto& n : g->nets)
-    if (n.eval_tc) bucket_tiles[n.F_PAD / 16] += (n.n_vox + kTcTile - 1) / kTcTile;
+    if (n.eval_tc && !is_lw(n)) bucket_tiles[n.F_PAD / 16] += (n.n_vox + kTcTile - 1) / kTcTile;
   for (int b = 1; b < kBuckets; ++b) g->tc_eval_tpb[b] = tc_eval_tpb(bucket_tiles[b], g->num_sms);
   for (int i = 0; i < g->n_nets; ++i) {
     const NetDev& n = g->nets[i];
+    if (is_lw(n)) continue;  // decoded by the layer-wise path, see below
     if (n.eval_tc) {
       const int b = n.F_PAD / 16;
       const long long tiles = (n.n_vox + kTcTile - 1) / kTcTile;
@@ -271,7 +343,26 @@ int build_eval_tables(BriefGroup* g, cudaStream_t st) {
   TableBuilder tb;
   tb.add(g->simt_eval, sp, sn);
   for (int b = 1; b < kBuckets; ++b) tb.add(g->tc_eval[b], tp[b], tn[b]);
-  return upload_tables(g->d_eval_tables, tb.tab, st);
+  RC(upload_tables(g->d_eval_tables, tb.tab, st));
+  // wide networks: the dense grid of a block is decoded in passes of at most `cap` tiles (two activation buffers)
+  g->lw_eval.clear();
+  for (int i = 0; i < g->n_nets; ++i) {
+    const NetDev& n = g->nets[i];
+    if (!is_lw(n)) continue;
+    const long long tiles = (n.n_vox + kTcTile - 1) / kTcTile;
+    const long long cap = std::max<long long>(g->num_sms, (long long)((size_t)1 << 30) / (long long)lw_tile_bytes_host(n.F_PAD));
+    for (long long first = 0; first < tiles; first += cap) {
+      LwPass p;
+      p.F = n.F_PAD;
+      p.L = n.L;
+      p.nets = {i};
+      p.tile_count = {(int)std::min<long long>(cap, tiles - first)};
+      if (first > 0x7fffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "block too large for the layer-wise decode");
+      p.tile_first = {(int)first};
+      g->lw_eval.push_back(p);
+    }
+  }
+  return upload_lw_tables(g->lw_eval, g->d_lw_eval_tab, g->d_lw_eval_base, g->num_sms, st);
 }
 
 // (re)build the fit decomposition: slices per network, partial arenas, block -> work tables
@@ -292,12 +383,12 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   drop_host_step_graphs(g);  // the captured launches carry the old decomposition
   for (int b = 0; b < kBuckets; ++b) g->tc_fit_L[b] = 0;
   for (auto& n : g->nets)
-    if (n.prec == BRIEF_PREC_F16) g->tc_fit_L[n.F_PAD / 16] = std::max(g->tc_fit_L[n.F_PAD / 16], n.L);
+    if (n.prec == BRIEF_PREC_F16 && !is_lw(n)) g->tc_fit_L[n.F_PAD / 16] = std::max(g->tc_fit_L[n.F_PAD / 16], n.L);
   // tensor-core networks: one CTA per slice; each width bucket is its own launch, so its slices are sized to fill
   // one wave of CTAs (SMs x resident CTAs of that bucket's kernel) by themselves
   long long tc_tiles[kBuckets] = {0}, tc_tps[kBuckets] = {0};
   for (auto& n : g->nets)
-    if (n.prec == BRIEF_PREC_F16) {
+    if (n.prec == BRIEF_PREC_F16 && !is_lw(n)) {
       const long long b = n.mode == BRIEF_SAMPLE_FULL_BLOCK ? n.n_vox : (long long)n.batch;
       tc_tiles[n.F_PAD / 16] += (b + kTcTile - 1) / kTcTile;
     }
@@ -307,7 +398,7 @@ int finalize(BriefGroup* g, cudaStream_t st) {
     tc_tps[b] = std::max<long long>(1, (tc_tiles[b] + wave - 1) / wave);
   }
   long long slice_total = 0, part_total = 0, idx_total = 0;
-  std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets], op{0}, on;
+  std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets], op{0}, on, lw_ids;
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
   for (int i = 0; i < g->n_nets; ++i) {
     NetDev& n = g->nets[i];
@@ -319,11 +410,13 @@ int finalize(BriefGroup* g, cudaStream_t st) {
       n.idx_off = idx_total;
       idx_total += n.batch;
     }
-    const bool tc = n.prec == BRIEF_PREC_F16;
-    const int tile = tc ? kTcTile : tm;
+    const bool lw = n.prec == BRIEF_PREC_F16 && is_lw(n);
+    const bool tc = n.prec == BRIEF_PREC_F16 && !lw;
+    const int tile = (tc || lw) ? kTcTile : tm;
     const long long n_tiles = ((long long)n.batch + tile - 1) / tile;
     const long long max_slices = std::max<long long>(1, (long long)(kPartialCapBytes / ((size_t)n.P_dev * 4)));
     long long tps = (n_tiles + max_slices - 1) / max_slices;
+    if (lw) tps = std::max<long long>(tps, (n_tiles + 7) / 8);  // layer-wise path: at most 8 slices (dW CTAs) per network, fixed by the network alone
     if (tc) {
       // PER_NETWORK: the network fills one wave by itself, so its slice boundaries (and with them the fp32
       // summation order of its gradients) do not depend on what else shares the GPU
@@ -339,7 +432,9 @@ int finalize(BriefGroup* g, cudaStream_t st) {
     n.part_off = part_total;
     slice_total += n.n_slices;
     part_total += (long long)n.n_slices * n.P_dev;
-    if (tc) {
+    if (lw) {
+      lw_ids.push_back(i);
+    } else if (tc) {
       const int b = n.F_PAD / 16;
       tn[b].push_back(i);
       tp[b].push_back(tp[b].back() + n.n_slices);
@@ -356,7 +451,40 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   for (int b = 1; b < kBuckets; ++b) tb.add(g->tc_fit[b], tp[b], tn[b]);
   tb.add(g->opt, op, on);
   RC(upload_tables(g->d_fit_tables, tb.tab, st));
+  // layer-wise passes: networks of one (F_PAD, L), greedily packed under the scratch budget
+  g->lw_fit.clear();
+  std::sort(lw_ids.begin(), lw_ids.end(), [&](int x, int y) {
+    const NetDev &a = g->nets[x], &b = g->nets[y];
+    return a.F_PAD != b.F_PAD ? a.F_PAD < b.F_PAD : a.L != b.L ? a.L < b.L : x < y;
+  });
+  size_t lw_bytes = 0;
+  for (int i : lw_ids) {
+    const NetDev& n = g->nets[i];
+    const int tiles = (int)(((long long)n.batch + kTcTile - 1) / kTcTile);
+    LwPass* p = g->lw_fit.empty() ? nullptr : &g->lw_fit.back();
+    long long cur = 0;
+    if (p) for (int c : p->tile_count) cur += c;
+    if (!p || p->F != n.F_PAD || p->L != n.L || (int)p->nets.size() >= g->num_sms ||
+        lw_scratch_bytes(n.F_PAD, n.L, cur + tiles) > kLwScratchBudget) {
+      g->lw_fit.emplace_back();
+      p = &g->lw_fit.back();
+      p->F = n.F_PAD;
+      p->L = n.L;
+      cur = 0;
+    }
+    p->nets.push_back(i);
+    p->tile_count.push_back(tiles);
+    p->tile_first.push_back(0);
+    p->max_slices = std::max(p->max_slices, n.n_slices);
+    lw_bytes = std::max(lw_bytes, lw_scratch_bytes(n.F_PAD, n.L, cur + tiles));
+  }
+  RC(upload_lw_tables(g->lw_fit, g->d_lw_fit_tab, g->d_lw_fit_base, g->num_sms, st));
+  for (const auto& p : g->lw_eval) lw_bytes = std::max(lw_bytes, lw_eval_scratch_bytes(p.F, p.T));
+  if (lw_bytes > 0) CU(g->d_lw_scratch.ensure(lw_bytes));
+  const size_t part_before = g->d_partials.n;
   CU(g->d_partials.ensure((size_t)part_total));
+  // the layer-wise kernels write only the real entries of a slot: the pads of the padded device layout must be zero
+  if (!lw_ids.empty() || g->d_partials.n != part_before) CU(cudaMemsetAsync(g->d_partials.p, 0, g->d_partials.n * sizeof(float), st));
   // wide tensor-core buckets: one activation stash + dW scratch per SM (buckets launch one after the other and share it)
   size_t stash_total = 0;
   g->stash_stride = 0;
@@ -385,6 +513,8 @@ int ensure_wpack(BriefGroup* g, cudaStream_t st) {
   g->wpack_dirty = false;
   return 0;
 }
+
+int launch_lw_fit(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st, const StepState* state);
 
 int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st,
                        const StepState* state = nullptr) {
@@ -417,6 +547,7 @@ int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uin
     a.TM = kTcTile;
     LAUNCH(launch_tc_fit(a, 16 * b, g->tc_fit_L[b], g->tc_fit[b].blocks, st));
   }
+  if (!g->lw_fit.empty()) RC(launch_lw_fit(g, dev_idx, seed, step, st, state));
   return 0;
 }
 
@@ -437,6 +568,100 @@ void step_scalars(int kind, double lr, double b1, double b2, long long t, float*
     *neg_clr = (float)(-(lr / (1.0 - std::pow(b1, (double)t))));
     *bc2_sqrt = (float)std::sqrt(1.0 - std::pow(b2, (double)t));
   }
+}
+
+// one training step of the wide networks, layer by layer (brief_tc_lw.cu)
+int launch_lw_fit(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st, const StepState* state) {
+  for (const LwPass& p : g->lw_fit) {
+    const int NH = p.L - 2, n = (int)p.nets.size();
+    LwArgs a{};
+    a.nets = g->d_nets.p;
+    a.scratch = g->d_lw_scratch.p;
+    a.wpack = g->d_wpack.p;
+    a.axes = g->d_axes.p;
+    a.idx = reinterpret_cast<const long long*>(dev_idx);
+    a.seed = seed;
+    a.step = step;
+    a.state = state;
+    a.partials = g->d_partials.p;
+    a.loss_partials = g->d_loss_partials.p;
+    auto off = [&](int what, int j) { return lw_fit_offset(p.F, p.L, p.T, what, j); };
+    lw_bind_tables(a, p, g->d_lw_fit_tab.p, g->d_lw_fit_base.p, false);
+    LAUNCH(launch_lw_sample_l0(a, (int)p.T, st));
+    for (int j = 1; j <= NH; ++j) {  // theta_j = ACT_{j-1} W'_j^T
+      lw_bind_tables(a, p, g->d_lw_fit_tab.p, g->d_lw_fit_base.p, true);
+      a.layer = j - 1;
+      a.in_off = off(0, j - 1);
+      a.out_off = off(0, j);
+      a.out2_off = off(1, j);
+      LAUNCH(launch_lw_gemm(a, 0, p.ctas(), st));
+    }
+    lw_bind_tables(a, p, g->d_lw_fit_tab.p, g->d_lw_fit_base.p, false);
+    a.in_off = off(0, NH);
+    a.out_off = off(2, 0);
+    LAUNCH(launch_lw_last(a, (int)p.T, st));
+    a.kind = 2;  // dWlast, dblast = ACT_NH^T [dy']
+    a.nb = 16;
+    a.in_off = off(0, NH);
+    a.in2_off = off(4, 0);
+    LAUNCH(launch_lw_dw(a, n, st));
+    int cur = 0;
+    for (int l = NH; l >= 1; --l) {
+      a.kind = 0;  // dW_l = DZ_l^T ACT_{l-1}
+      a.nb = p.F;
+      a.layer = l;
+      a.in_off = off(2, cur);
+      a.in2_off = off(0, l - 1);
+      LAUNCH(launch_lw_dw(a, n, st));
+      lw_bind_tables(a, p, g->d_lw_fit_tab.p, g->d_lw_fit_base.p, true);
+      a.layer = l - 1;  // dz_{l-1} = (DZ_l W'_l) * COS_{l-1}
+      a.in_off = off(2, cur);
+      a.in2_off = off(1, l - 1);
+      a.out_off = off(2, cur ^ 1);
+      LAUNCH(launch_lw_gemm(a, 2, p.ctas(), st));
+      lw_bind_tables(a, p, g->d_lw_fit_tab.p, g->d_lw_fit_base.p, false);
+      cur ^= 1;
+    }
+    a.kind = 1;  // dW0, db0 = DZ_0^T [x_hi 1 x_lo ...]
+    a.nb = 16;
+    a.in_off = off(2, cur);
+    a.in2_off = off(3, 0);
+    LAUNCH(launch_lw_dw(a, n, st));
+    LAUNCH(launch_lw_loss_reduce(a, n, st));
+  }
+  return 0;
+}
+
+// forward of one pass of the wide networks' decode (dense grid or explicit coordinates)
+int launch_lw_eval(BriefGroup* g, const LwPass& p, const int* tab, const long long* base, const float* coords, long long n_coords,
+                   float* out_f32, float* layers_out, void* const* out_ptrs, int out_dtype, cudaStream_t st) {
+  const int NH = p.L - 2;
+  LwArgs a{};
+  a.nets = g->d_nets.p;
+  a.scratch = g->d_lw_scratch.p;
+  a.wpack = g->d_wpack.p;
+  a.axes = g->d_axes.p;
+  a.eval = 1;
+  a.coords = coords;
+  a.n_coords = n_coords;
+  a.out_f32 = out_f32;
+  a.layers_out = layers_out;
+  a.out_ptrs = out_ptrs;
+  a.out_dtype = out_dtype;
+  const size_t buf = (size_t)p.T * lw_tile_bytes_host(p.F);
+  lw_bind_tables(a, p, tab, base, false);
+  LAUNCH(launch_lw_sample_l0(a, (int)p.T, st));  // -> buffer 0
+  for (int j = 1; j <= NH; ++j) {
+    lw_bind_tables(a, p, tab, base, true);
+    a.layer = j - 1;
+    a.in_off = (size_t)((j - 1) & 1) * buf;
+    a.out_off = (size_t)(j & 1) * buf;
+    LAUNCH(launch_lw_gemm(a, 1, p.ctas(), st));
+  }
+  lw_bind_tables(a, p, tab, base, false);
+  a.in_off = (size_t)(NH & 1) * buf;
+  LAUNCH(launch_lw_last(a, (int)p.T, st));
+  return 0;
 }
 
 int launch_opt_kernel(BriefGroup* g, bool from_partials, bool apply, int kind, double lr, double b1, double b2,
@@ -567,7 +792,8 @@ int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device
     n.prec = (precision == BRIEF_PREC_FP32 || !tc_ok) ? BRIEF_PREC_FP32 : BRIEF_PREC_F16;
     // forward / decompress have a wider tensor-core envelope than the fit (no activation ring): AUTO uses it
     n.eval_tc = (n.prec == BRIEF_PREC_F16 ||
-                 (precision == BRIEF_PREC_AUTO && tc_eval_supported(n.f, n.L, n.in_dim, n.out_dim))) ? 1 : 0;
+                 (precision == BRIEF_PREC_AUTO && (tc_eval_supported(n.f, n.L, n.in_dim, n.out_dim) ||
+                                                   tc_lw_supported(n.f, n.L, n.in_dim, n.out_dim)))) ? 1 : 0;
     if (n.eval_tc) {
       n.F_PAD = tc_fpad(n.f);
       n.wpack_off = (long long)g->total_wpack;
@@ -617,8 +843,11 @@ void brief_group_destroy(BriefGroup* g) {
   if (!g) return;
   cudaSetDevice(g->device);
   drop_host_step_graphs(g);
+  if (g->capture_stream) cudaStreamDestroy(g->capture_stream);
   g->d_nets.release(); g->d_params.release(); g->d_grads.release(); g->d_m.release(); g->d_v.release();
   g->d_axes.release(); g->d_partials.release(); g->d_loss_partials.release(); g->d_loss_scratch.release();
+  g->d_lw_fit_tab.release(); g->d_lw_eval_tab.release(); g->d_lw_fit_base.release(); g->d_lw_eval_base.release();
+  g->d_lw_scratch.release();
   g->d_wpack.release(); g->d_stash.release(); g->d_fit_tables.release(); g->d_eval_tables.release(); g->d_outptrs.release();
   delete g;
 }
@@ -858,10 +1087,13 @@ int brief_fit_step_host(BriefGroup* g, const int64_t* host_idx, const BriefOptCo
     if (!no_graph) {
       // capture the same sequence a plain submission would enqueue (relaxed mode: the launchers call cudaFuncSetAttribute)
       cudaGraph_t graph = nullptr;
-      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed);
+      if (!g->capture_stream) CU(cudaStreamCreateWithFlags(&g->capture_stream, cudaStreamNonBlocking));
+      CU(cudaStreamSynchronize(st));  // finalize / pack above ran on the caller's stream
+      cudaStream_t cs = g->capture_stream;
+      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed);
       if (e == cudaSuccess) {
-        int rc = enqueue_host_step(g, *h, n_idx, st, &h->kernels);
-        e = cudaStreamEndCapture(st, &graph);
+        int rc = enqueue_host_step(g, *h, n_idx, cs, &h->kernels);
+        e = cudaStreamEndCapture(cs, &graph);
         if (rc != 0 || e != cudaSuccess || !graph) {
           if (graph) cudaGraphDestroy(graph);
           cudaGetLastError();
@@ -936,6 +1168,33 @@ int brief_forward(BriefGroup* g, int32_t net, const float* dev_coords, int64_t n
   a.out_f32 = dev_out;
   a.layers_out = dev_layers;
   a.wpack = g->d_wpack.p;
+  if (is_lw(nd)) {  // wide network: layer-wise forward over passes of explicit coordinates
+    RC(ensure_wpack(g, st));
+    const long long tiles = (n + kTcTile - 1) / kTcTile;
+    const long long cap = std::max<long long>(g->num_sms, (long long)((size_t)1 << 30) / (long long)lw_tile_bytes_host(nd.F_PAD));
+    std::vector<LwPass> passes;
+    for (long long first = 0; first < tiles; first += cap) {
+      LwPass p;
+      p.F = nd.F_PAD;
+      p.L = nd.L;
+      p.nets = {net};
+      p.tile_count = {(int)std::min<long long>(cap, tiles - first)};
+      p.tile_first = {(int)first};
+      passes.push_back(p);
+    }
+    DevBuf<int> tab;
+    DevBuf<long long> base;
+    int rc = upload_lw_tables(passes, tab, base, g->num_sms, st);
+    size_t need = 0;
+    for (const auto& p : passes) need = std::max(need, lw_eval_scratch_bytes(p.F, p.T));
+    if (!rc && g->d_lw_scratch.ensure(need) != cudaSuccess) rc = fail(BRIEF_ERR_CUDA, "alloc layer-wise scratch");
+    for (size_t i = 0; i < passes.size() && !rc; ++i)
+      rc = launch_lw_eval(g, passes[i], tab.p, base.p, dev_coords, n, dev_out, dev_layers, nullptr, 0, st);
+    cudaStreamSynchronize(st);  // the temporary tables are freed below
+    tab.release();
+    base.release();
+    return rc;
+  }
   if (nd.eval_tc) {
     RC(ensure_wpack(g, st));
     const long long tiles = (n + kTcTile - 1) / kTcTile;
@@ -990,6 +1249,16 @@ int brief_decompress(BriefGroup* g, void* const* host_dev_out, int32_t out_dtype
     a.TM = kTcTile;
     a.tiles_per_block = g->tc_eval_tpb[b];
     LAUNCH(launch_tc_eval(a, 16 * b, g->tc_L[b], g->tc_eval[b].blocks, st));
+  }
+  for (const LwPass& p : g->lw_eval) {  // wide networks, layer by layer
+    if (host_dev_out[p.nets[0]] == nullptr) continue;
+    if (!packed) { RC(ensure_wpack(g, st)); packed = true; }
+    size_t need = lw_eval_scratch_bytes(p.F, p.T);
+    if (g->d_lw_scratch.n < need) {
+      CU(cudaStreamSynchronize(st));
+      CU(g->d_lw_scratch.ensure(need));
+    }
+    RC(launch_lw_eval(g, p, g->d_lw_eval_tab.p, g->d_lw_eval_base.p, nullptr, 0, nullptr, nullptr, g->d_outptrs.p, out_dtype, st));
   }
   return 0;
 }

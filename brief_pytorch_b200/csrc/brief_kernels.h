@@ -61,6 +61,39 @@ struct FitArgs {
   const StepState* state;   // non-NULL: `step` is read from device memory (graph replay)
 };
 
+// Layer-wise tensor-core path for wide networks (brief_tc_lw.cu): one pass = a set of networks of one padded width whose
+// tiles share a scratch arena.  Work entry i = network work_net[i], tiles [tile_first[i], tile_first[i] + tile_count[i])
+// of it, stored at scratch tiles tile_base[i]...; `work_prefix` is the launch's block -> entry table (tiles for the
+// per-tile kernels, CTAs for the GEMM kernel).
+struct LwArgs {
+  const NetDev* nets;
+  const int* work_prefix;
+  const int* work_net;
+  const int* tile_count;
+  const long long* tile_base;
+  const int* tile_first;
+  int n_work;
+  int F;              // padded width of the bucket
+  long long T;        // tiles of the pass (scratch tensor stride)
+  int layer;          // hidden-layer index of this launch (weights at image offset layer * F * F * 2)
+  int kind, nb, max_slices, eval;
+  size_t in_off, in2_off, out_off, out2_off;  // scratch byte offsets of the launch's tile tensors
+  unsigned char* scratch;
+  const unsigned char* wpack;
+  const float* axes;
+  const long long* idx;
+  uint64_t seed, step;
+  const StepState* state;
+  const float* coords;    // explicit-coordinate forward
+  long long n_coords;
+  float* out_f32;
+  float* layers_out;
+  void* const* out_ptrs;
+  int out_dtype;
+  float* partials;
+  float* loss_partials;
+};
+
 // Optimiser step over the whole group (one launch).
 struct OptArgs {
   const NetDev* nets;
@@ -136,5 +169,17 @@ bool tc_eval_supported(int f, int L, int in_dim, int out_dim);
 size_t tc_fit_smem(int F_PAD, int L);
 cudaError_t launch_tc_eval(const EvalArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st);
 cudaError_t launch_tc_fit(const FitArgs& a, int F_PAD, int L_max, int n_blocks, cudaStream_t st);
+
+// brief_tc_lw.cu (layer-wise tcgen05 path, 128 < F_PAD <= 256)
+bool tc_lw_supported(int f, int L, int in_dim, int out_dim);
+size_t lw_scratch_bytes(int F, int L, long long T);
+size_t lw_eval_scratch_bytes(int F, long long T);
+size_t lw_tile_bytes_host(int F);
+size_t lw_fit_offset(int F, int L, long long T, int what, int j);  // what: 0 ACT_j, 1 COS_j, 2 DZ_j, 3 X block, 4 DY block
+cudaError_t launch_lw_sample_l0(const LwArgs& a, int n_tiles, cudaStream_t st);
+cudaError_t launch_lw_gemm(const LwArgs& a, int mode, int n_ctas, cudaStream_t st);
+cudaError_t launch_lw_last(const LwArgs& a, int n_tiles, cudaStream_t st);
+cudaError_t launch_lw_dw(const LwArgs& a, int n_nets, cudaStream_t st);
+cudaError_t launch_lw_loss_reduce(const LwArgs& a, int n_nets, cudaStream_t st);
 
 }  // namespace brief

@@ -216,8 +216,7 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
               for (int i = 0; i < 16; ++i)
                 if (16 * c + i < n.f) zdump[16 * c + i] = vc[i] * inv;
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
+            sin_chunk16(vc, 16 * c, n.f);
             store_chunk16(sAct, r, c, vc);
           }
           signal(u);
@@ -607,8 +606,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           tmem_ld_wait();
           if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
+          sin_chunk16(vc, 16 * (c_base + c), f);
           store_chunk16_both<false>(dst, r, c_base + c, vc, ts && st < NH, my_af + 8 * c);
           if (st == NH) {
 #pragma unroll
@@ -661,11 +659,17 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           tmem_ld_wait();
           if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
+          if (16 * (c_base + c) + 16 <= f) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
-            vc[i] = dys * w4.x * fast_cos(vc[i]); vc[i + 1] = dys * w4.y * fast_cos(vc[i + 1]);
-            vc[i + 2] = dys * w4.z * fast_cos(vc[i + 2]); vc[i + 3] = dys * w4.w * fast_cos(vc[i + 3]);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
+              vc[i] = dys * w4.x * fast_cos(vc[i]); vc[i + 1] = dys * w4.y * fast_cos(vc[i + 1]);
+              vc[i + 2] = dys * w4.z * fast_cos(vc[i + 2]); vc[i + 3] = dys * w4.w * fast_cos(vc[i + 3]);
+            }
+          } else {  // Wlast is zero beyond column f-1: the bias and pad columns need no cosine
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              vc[i] = 16 * (c_base + c) + i < f ? dys * s_wl[16 * (c_base + c) + i] * fast_cos(vc[i]) : 0.0f;
           }
           store_chunk16_both<true>(dzb, r, c_base + c, vc, ts, my_ad + 8 * c);
         }
@@ -705,8 +709,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           }
           float* z = vz[c & 1];
           const float* x = vx[c & 1];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
+          cos_mul_chunk16(z, x, scale, 16 * (c_base + c), f);
           store_chunk16_both<true>(dzb, r, c_base + c, z, ts && l >= 2, my_ad + 8 * c);
         }
         TT(a2);
@@ -839,6 +842,7 @@ int tc_fit_ctas_per_sm(int F, int L) {
 bool tc_supported(int f, int L, int in_dim, int out_dim) {
   const int F = tc_fpad(f);
   if (out_dim != 1 || (in_dim != 2 && in_dim != 3)) return false;
+  if (F > 128) return tc_lw_supported(f, L, in_dim, out_dim);  // layer-wise path (brief_tc_lw.cu)
   if (F > 64) return tc_wide_supported(f, L, in_dim, out_dim);
   if (L < 3 || F > 64) return false;
   if (3 * F + fit_acc_blocks(L - 2) * F > 512) return false;  // TMEM: Zf, Zb (x2 if it fits), Xb + packed dW accumulators

@@ -58,6 +58,35 @@ __device__ __forceinline__ float fast_sin(float x) { return __sinf(x); }
 __device__ __forceinline__ float fast_cos(float x) { return __cosf(x); }
 #endif
 
+// Sines of one 16-column chunk of a row whose first column is `col0`, for a network of width f (F_PAD >= f + 2):
+// columns < f take the special-function unit; columns f, f+1 are the constant-one bias columns (sin(pi/2), written as
+// the literal 1.0 — the same fp16 operand); the zero pads beyond stay zero.  f is CTA-uniform, so a chunk of real
+// columns runs the plain unrolled loop and only the boundary chunk is predicated: at f = 56 (F_PAD = 64) this is
+// 56 instead of 64 MUFU per row and layer.
+__device__ __forceinline__ void sin_chunk16(float* v, int col0, int f) {
+  if (col0 + 16 <= f) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fast_sin(v[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int col = col0 + i;
+      v[i] = col < f ? fast_sin(v[i]) : (col < f + 2 ? 1.0f : 0.0f);
+    }
+  }
+}
+
+// dz = dX * scale * cos(theta) for one 16-column chunk; columns >= f (bias columns: cos(pi/2), pads: dX = 0) are zero
+__device__ __forceinline__ void cos_mul_chunk16(float* z, const float* x, float scale, int col0, int f) {
+  if (col0 + 16 <= f) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = col0 + i < f ? x[i] * scale * fast_cos(z[i]) : 0.0f;
+  }
+}
+
 // first layer for 8 consecutive features of one sample -> 4 packed f16x2 words (optionally the raw z)
 template <bool WITH_Z>
 __device__ __forceinline__ uint4 first_layer8(const float4* __restrict__ w0b, int c0, float x0, float x1, float x2,
@@ -112,6 +141,16 @@ __device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_buf, uint32_t b_
   constexpr uint32_t idesc = make_idesc(64, N, true, true);
 #pragma unroll
   for (int k = 0; k < kTile / 16; ++k)
+    mma_f16(d, make_desc(a_buf + k * 2 * 128, 128, kActLBO), make_desc(b_buf + k * 2 * 128, 128, kActLBO), idesc,
+            (accumulate || k > 0) ? 1u : 0u);
+}
+
+// K-steps [k0, k1) of the same contraction (the MMA-issue warp of the fit kernel splits a dW into two halves so that a
+// forward batch that becomes ready in between does not wait for all eight)
+template <int N>
+__device__ __forceinline__ void issue_dw_range(uint32_t d, uint32_t a_buf, uint32_t b_buf, bool accumulate, int k0, int k1) {
+  constexpr uint32_t idesc = make_idesc(64, N, true, true);
+  for (int k = k0; k < k1; ++k)
     mma_f16(d, make_desc(a_buf + k * 2 * 128, 128, kActLBO), make_desc(b_buf + k * 2 * 128, 128, kActLBO), idesc,
             (accumulate || k > 0) ? 1u : 0u);
 }
