@@ -968,9 +968,9 @@ def main():
             "e2e": {"value": samples_per_step * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "gpu_launches": int(e2e_launches),
-                    "note": "per step ONE call SirenGroup.fit_step_host = one CUDA-graph launch: [pinned host sampler indices + "
-                            "step scalars -> device] -> fit kernel -> optimiser kernel -> [per-block loss -> pinned host]; the "
-                            "host reads every step's loss, one step behind the GPU"},
+                    "note": "per step ONE call SirenGroup.fit_step_host: pinned host sampler indices + step scalars -> device on "
+                            "a copy stream (under the previous step's kernels), then one CUDA-graph launch: fit kernel -> optimiser "
+                            "kernel -> per-block loss -> pinned host; the host reads every step's loss, one step behind the GPU"},
             "gpu_launches": int(launches_total),
             "roofline": {"bound": "tensor", "achieved": tf_kernel, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": tf_kernel / peak_tf,

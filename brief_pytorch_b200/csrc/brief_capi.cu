@@ -102,6 +102,7 @@ struct HostStepGraph {
   uint64_t seed = 0;
   cudaGraphExec_t exec = nullptr;
   cudaEvent_t done = nullptr;      // completion of the slot's last submission (its pinned scalars may be rewritten after it)
+  cudaEvent_t copied = nullptr;    // this submission's inputs have arrived (copy stream)
   StepState* h_state = nullptr;    // pinned
   StepState* d_state = nullptr;
   long long* d_idx = nullptr;
@@ -126,6 +127,7 @@ struct BriefGroup {
   int nsmid = 0;            // PTX %nsmid, queried when a wide tensor-core bucket first needs its per-SM scratch
   HostStepGraph host_steps[kHostStepSlots];
   int host_step_next = 0;
+  cudaStream_t copy_stream = nullptr;     // host -> device copies of brief_fit_step_host (under the previous step's kernels)
   cudaStream_t capture_stream = nullptr;  // step graphs are captured here (the caller's stream may be the legacy default
                                           // stream, which cannot be captured) and launched into the caller's stream
   int n_nets = 0;
@@ -293,6 +295,7 @@ struct TableBuilder {
 void drop_host_step_graph(HostStepGraph& h) {
   if (h.exec) cudaGraphExecDestroy(h.exec);
   if (h.done) cudaEventDestroy(h.done);
+  if (h.copied) cudaEventDestroy(h.copied);
   if (h.h_state) cudaFreeHost(h.h_state);
   if (h.d_state) cudaFree(h.d_state);
   if (h.d_idx) cudaFree(h.d_idx);
@@ -400,6 +403,8 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   long long slice_total = 0, part_total = 0, idx_total = 0;
   std::vector<int> sp{0}, sn, tp[kBuckets], tn[kBuckets], op{0}, on, lw_ids;
   for (int b = 0; b < kBuckets; ++b) tp[b].push_back(0);
+  int n_lw = 0;
+  for (const auto& n : g->nets) n_lw += (n.prec == BRIEF_PREC_F16 && is_lw(n)) ? 1 : 0;
   for (int i = 0; i < g->n_nets; ++i) {
     NetDev& n = g->nets[i];
     if (n.mode == BRIEF_SAMPLE_FULL_BLOCK) {
@@ -416,7 +421,15 @@ int finalize(BriefGroup* g, cudaStream_t st) {
     const long long n_tiles = ((long long)n.batch + tile - 1) / tile;
     const long long max_slices = std::max<long long>(1, (long long)(kPartialCapBytes / ((size_t)n.P_dev * 4)));
     long long tps = (n_tiles + max_slices - 1) / max_slices;
-    if (lw) tps = std::max<long long>(tps, (n_tiles + 7) / 8);  // layer-wise path: at most 8 slices (dW CTAs) per network, fixed by the network alone
+    if (lw) {
+      // layer-wise path: a slice is one dW CTA per output half.  PER_NETWORK: 8 slices, fixed by the network alone;
+      // FILL_WAVE: enough slices for the wide networks of the group to fill the SMs together (2 CTAs per slice)
+      long long want = 8;
+      if (g->slicing != BRIEF_SLICING_PER_NETWORK)
+        want = std::min<long long>(24, std::max<long long>(8, (g->num_sms + 2 * n_lw - 1) / (2 * std::max(1, n_lw))));
+      want = std::min<long long>(want, std::max<long long>(1, (long long)((size_t)(32u << 20) / ((size_t)n.P_dev * 4))));
+      tps = std::max<long long>((n_tiles + want - 1) / want, 1);
+    }
     if (tc) {
       // PER_NETWORK: the network fills one wave by itself, so its slice boundaries (and with them the fp32
       // summation order of its gradients) do not depend on what else shares the GPU
@@ -844,6 +857,7 @@ void brief_group_destroy(BriefGroup* g) {
   cudaSetDevice(g->device);
   drop_host_step_graphs(g);
   if (g->capture_stream) cudaStreamDestroy(g->capture_stream);
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
   g->d_nets.release(); g->d_params.release(); g->d_grads.release(); g->d_m.release(); g->d_v.release();
   g->d_axes.release(); g->d_partials.release(); g->d_loss_partials.release(); g->d_loss_scratch.release();
   g->d_lw_fit_tab.release(); g->d_lw_eval_tab.release(); g->d_lw_fit_base.release(); g->d_lw_eval_base.release();
@@ -1040,10 +1054,9 @@ int brief_fit_run(BriefGroup* g, const BriefOptConfig* cfg, uint64_t seed, int64
 }
 
 // ---- one training step driven from HOST buffers, replayed as a CUDA graph --------------------------------------------
+// kernels + loss read-back of one step (this is what the graph holds); the inputs arrive on the copy stream
 static int enqueue_host_step(BriefGroup* g, HostStepGraph& h, long long n_idx, cudaStream_t st, int* kernels) {
   const BriefOptConfig& c = h.cfg;
-  CU(cudaMemcpyAsync(h.d_state, h.h_state, sizeof(StepState), cudaMemcpyHostToDevice, st));
-  if (n_idx > 0) CU(cudaMemcpyAsync(h.d_idx, h.host_idx, (size_t)n_idx * sizeof(long long), cudaMemcpyHostToDevice, st));
   const long long before = g_launches.load();
   RC(launch_fit_kernels(g, n_idx > 0 ? reinterpret_cast<const int64_t*>(h.d_idx) : nullptr, h.seed, 0, st, h.d_state));
   RC(launch_opt_kernel(g, true, true, c.kind, c.lr, c.beta1, c.beta2, c.eps, 1, h.d_loss, st, h.d_state));
@@ -1067,6 +1080,8 @@ int brief_fit_step_host(BriefGroup* g, const int64_t* host_idx, const BriefOptCo
   for (const auto& n : g->nets)
     if (n.mode == BRIEF_SAMPLE_RANDOM_POINTS) n_idx += n.batch;
   if (!host_idx) n_idx = 0;  // on-device sampler stream (Philox, keyed by seed and step)
+  if (!g->capture_stream) CU(cudaStreamCreateWithFlags(&g->capture_stream, cudaStreamNonBlocking));
+  if (!g->copy_stream) CU(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
   // slot lookup: same buffers, stream and optimiser constants -> the cached graph is valid
   HostStepGraph* h = nullptr;
   for (auto& c : g->host_steps)
@@ -1083,36 +1098,41 @@ int brief_fit_step_host(BriefGroup* g, const int64_t* host_idx, const BriefOptCo
     CU(cudaMalloc(&h->d_loss, sizeof(float) * g->n_nets));
     if (n_idx > 0) CU(cudaMalloc(&h->d_idx, (size_t)n_idx * sizeof(long long)));
     CU(cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->copied, cudaEventDisableTiming));
     static const bool no_graph = getenv("BRIEF_NO_GRAPH") != nullptr;
     if (!no_graph) {
-      // capture the same sequence a plain submission would enqueue (relaxed mode: the launchers call cudaFuncSetAttribute)
+      // capture the sequence a plain submission would enqueue (relaxed mode: the launchers call cudaFuncSetAttribute), on
+      // an internal stream: the caller's stream may be the legacy default stream, which cannot be captured
       cudaGraph_t graph = nullptr;
-      if (!g->capture_stream) CU(cudaStreamCreateWithFlags(&g->capture_stream, cudaStreamNonBlocking));
       CU(cudaStreamSynchronize(st));  // finalize / pack above ran on the caller's stream
       cudaStream_t cs = g->capture_stream;
       cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed);
-      if (e == cudaSuccess) {
-        int rc = enqueue_host_step(g, *h, n_idx, cs, &h->kernels);
-        e = cudaStreamEndCapture(cs, &graph);
-        if (rc != 0 || e != cudaSuccess || !graph) {
-          if (graph) cudaGraphDestroy(graph);
-          cudaGetLastError();
-          return rc ? rc : fail(BRIEF_ERR_CUDA, "capturing the step graph failed: %s", cudaGetErrorString(e));
-        }
-        g_launches.fetch_add(-(long long)h->kernels);  // captured, not launched
-        e = cudaGraphInstantiate(&h->exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-      } else {
-        return fail(BRIEF_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+      if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+      int rc = enqueue_host_step(g, *h, n_idx, cs, &h->kernels);
+      e = cudaStreamEndCapture(cs, &graph);
+      if (rc != 0 || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return rc ? rc : fail(BRIEF_ERR_CUDA, "capturing the step graph failed: %s", cudaGetErrorString(e));
       }
+      g_launches.fetch_add(-(long long)h->kernels);  // captured, not launched
+      e = cudaGraphInstantiate(&h->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
     }
   }
   // this step's scalars: sampler stream position and the optimiser's step-dependent factors (host doubles like torch)
   const int64_t t = steps_done + 1;
-  CU(cudaEventSynchronize(h->done));  // the slot's previous submission has consumed its pinned scalars
+  CU(cudaEventSynchronize(h->done));  // the slot's previous submission has consumed its device buffers and pinned scalars
   h->h_state->step = (unsigned long long)(t - 1);
   step_scalars(cfg->kind, lr_at(cfg, t), cfg->beta1, cfg->beta2, t, &h->h_state->neg_clr, &h->h_state->bc2_sqrt);
+  // inputs cross PCIe on the copy stream, i.e. under the kernels of the step before (the caller enqueues step s while
+  // step s-1 runs); the kernels of this step wait for them
+  CU(cudaMemcpyAsync(h->d_state, h->h_state, sizeof(StepState), cudaMemcpyHostToDevice, g->copy_stream));
+  if (n_idx > 0)
+    CU(cudaMemcpyAsync(h->d_idx, host_idx, (size_t)n_idx * sizeof(long long), cudaMemcpyHostToDevice, g->copy_stream));
+  CU(cudaEventRecord(h->copied, g->copy_stream));
+  CU(cudaStreamWaitEvent(st, h->copied, 0));
   if (h->exec) {
     CU(cudaGraphLaunch(h->exec, st));
     g_launches.fetch_add(h->kernels);

@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
               for (int i = 0; i < 16; ++i)
                 if (16 * c + i < n.f) zdump[16 * c + i] = vc[i] * inv;
             }
-            sin_chunk16(vc, 16 * c, n.f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
             store_chunk16(sAct, r, c, vc);
           }
           signal(u);
@@ -606,7 +607,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           tmem_ld_wait();
           if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
-          sin_chunk16(vc, 16 * (c_base + c), f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
           store_chunk16_both<false>(dst, r, c_base + c, vc, ts && st < NH, my_af + 8 * c);
           if (st == NH) {
 #pragma unroll
@@ -659,17 +661,11 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           tmem_ld_wait();
           if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
-          if (16 * (c_base + c) + 16 <= f) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
-              vc[i] = dys * w4.x * fast_cos(vc[i]); vc[i + 1] = dys * w4.y * fast_cos(vc[i + 1]);
-              vc[i + 2] = dys * w4.z * fast_cos(vc[i + 2]); vc[i + 3] = dys * w4.w * fast_cos(vc[i + 3]);
-            }
-          } else {  // Wlast is zero beyond column f-1: the bias and pad columns need no cosine
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              vc[i] = 16 * (c_base + c) + i < f ? dys * s_wl[16 * (c_base + c) + i] * fast_cos(vc[i]) : 0.0f;
+          for (int i = 0; i < 16; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
+            vc[i] = dys * w4.x * fast_cos(vc[i]); vc[i + 1] = dys * w4.y * fast_cos(vc[i + 1]);
+            vc[i + 2] = dys * w4.z * fast_cos(vc[i + 2]); vc[i + 3] = dys * w4.w * fast_cos(vc[i + 3]);
           }
           store_chunk16_both<true>(dzb, r, c_base + c, vc, ts, my_ad + 8 * c);
         }
@@ -709,7 +705,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           }
           float* z = vz[c & 1];
           const float* x = vx[c & 1];
-          cos_mul_chunk16(z, x, scale, 16 * (c_base + c), f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
           store_chunk16_both<true>(dzb, r, c_base + c, z, ts && l >= 2, my_ad + 8 * c);
         }
         TT(a2);

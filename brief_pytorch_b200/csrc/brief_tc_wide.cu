@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
         tmem_ld_wait();
         if (c + 1 < c_hi) tmem_ld16(TZ + lane_base + 16 * (c + 1), vb[(ci + 1) & 1]);  // under this chunk's sines
         float* v = vb[ci & 1];
-        sin_chunk16(v, 16 * c, f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fast_sin(v[i]);
         const uint4 lo4 = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
         const uint4 hi4 = make_uint4(pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]), pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
         const uint32_t o0 = chunk_off(r, 2 * c, kTile), o1 = chunk_off(r, 2 * c + 1, kTile);
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
       tmem_ld16(TZ + lane_base + 16 * c, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = 16 * c + i < f ? dys * s_wl[16 * c + i] * fast_cos(v[i]) : 0.0f;
+      for (int i = 0; i < 16; ++i) v[i] = dys * s_wl[16 * c + i] * fast_cos(v[i]);
       store_chunk16_both<true>(sDz, r, c, v, false, 0);
     }
     if (cg == 0) {
@@ -362,7 +363,8 @@ __global__ void __launch_bounds__(kWideThreads, 1) tc_fit_wide_kernel(FitArgs a)
           }
           float* z = zb[ci & 1];
           const float* x = xb[ci & 1];
-          cos_mul_chunk16(z, x, scale, 16 * c, f);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[i] = x[i] * scale * fast_cos(z[i]);
           store_chunk16_both<true>(dzb, r, c, z, false, 0);
         }
       }

@@ -176,9 +176,9 @@ int brief_fit_run(BriefGroup* g, const BriefOptConfig* cfg, uint64_t seed, int64
                   float* dev_loss_hist, void* stream);
 
 /* The loop body of main.py:385-401 for ONE step with HOST buffers — what a caller that draws the sampler indices with
- * the CPU generator (main.py:156) and reads loss.item() every step (main.py:401) needs — enqueued on `stream` as ONE
- * CUDA-graph launch: [host->device: step scalars, sampler indices] -> fit kernel(s) -> optimiser kernel ->
- * [device->host: per-network loss].  host_idx: PINNED host memory, int64, all RANDOM_POINTS networks' indices
+ * the CPU generator (main.py:156) and reads loss.item() every step (main.py:401) needs — enqueued as: [host->device: step scalars,
+ * sampler indices] on an internal copy stream (so that they cross PCIe under the kernels of the step before), then ONE
+ * CUDA-graph launch on `stream`: fit kernel(s) -> optimiser kernel -> [device->host: per-network loss].  host_idx: PINNED host memory, int64, all RANDOM_POINTS networks' indices
  * concatenated in network order (NULL: on-device sampler stream keyed by seed and step); host_loss: PINNED host
  * memory, n_nets floats, or NULL.  `steps_done` completed steps precede this one (optimiser step count, MultiStepLR
  * position, sampler stream position).  The call returns as soon as the step is enqueued; the caller synchronises on

@@ -125,19 +125,20 @@ def test_zero_length_and_error_paths():
     with pytest.raises(_cabi.BriefError) as e:      # data_channel 3 is outside the fused kernels
         SirenGroup([NetSpec(13, 5, 20.0, (4, 4, 4), 3, 3)], 0, "auto")
     assert e.value.code == -3
-    with pytest.raises(_cabi.BriefError) as e:      # explicit f16 for a width the fused fit kernel does not cover
-        SirenGroup([NetSpec(200, 7, 10.0, (4, 4, 4))], 0, "f16")
+    with pytest.raises(_cabi.BriefError) as e:      # explicit f16 for a width no tensor-core fit kernel covers (F_PAD > 256)
+        SirenGroup([NetSpec(300, 7, 10.0, (4, 4, 4))], 0, "f16")
     assert e.value.code == -3
     with pytest.raises(_cabi.BriefError):           # zero networks
         SirenGroup([], 0, "auto")
     # envelope of the tensor-core fit kernels under "auto": fused kernel up to f = 62, wide kernel up to f = 126
-    # (F_PAD = f + 2 rounded up to 16 <= 128), fp32 CUDA-core kernels beyond; the decode kernel follows the same F_PAD
-    for f, want in ((62, "f16"), (63, "f16"), (126, "f16"), (127, "fp32"), (228, "fp32")):
+    # (F_PAD = f + 2 rounded up to 16 <= 128), layer-wise kernels up to f = 254 (F_PAD <= 256: neuron.yaml as shipped,
+    # f = 228), fp32 CUDA-core kernels beyond; the decode follows the same F_PAD
+    for f, want in ((62, "f16"), (63, "f16"), (126, "f16"), (127, "f16"), (228, "f16"), (254, "f16")):
         g = SirenGroup([NetSpec(f, 7, 10.0, (4, 4, 4))], 0, "auto")
         assert g.precision(0) == want, (f, g.precision(0))
         g.close()
-    with pytest.raises(_cabi.BriefError) as e:      # f = 127 has no tensor-core fit kernel
-        SirenGroup([NetSpec(127, 7, 10.0, (4, 4, 4))], 0, "f16")
+    with pytest.raises(_cabi.BriefError) as e:      # f = 255 has no tensor-core fit kernel
+        SirenGroup([NetSpec(255, 7, 10.0, (4, 4, 4))], 0, "f16")
     assert e.value.code == -3
 
 

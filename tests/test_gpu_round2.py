@@ -35,17 +35,18 @@ def _small_group(prec="f16", n=2, f=24, L=5, dims=(24, 40, 40), batch=3000):
 @pytest.mark.parametrize("prec", ["f16", "fp32"])
 @pytest.mark.parametrize("host_indices", [True, False])
 def test_graphed_host_step_equals_separate_launches(prec, host_indices):
-    """brief_fit_step_host (one CUDA-graph launch: h2d scalars + indices, fit, optimiser, d2h loss) must leave exactly the
-    parameters and report exactly the losses of brief_fit_step + brief_opt_step on the same indices / sampler stream,
-    across MultiStepLR milestones."""
-    n, batch, steps, ms = 2, 3000, 7, [2, 4]
+    """brief_fit_step_host (inputs on the copy stream, then one CUDA-graph launch: fit, optimiser, d2h loss) must report
+    exactly the losses and leave exactly the parameters of brief_fit_step + brief_opt_step on the same indices / sampler
+    stream.  After a MultiStepLR milestone the two paths form the learning rate differently (brief_opt_step takes it as
+    a float, the graphed step keeps torch's chained double product), so from there on the comparison is to 1e-5; the
+    device-sampler variant is also compared bit for bit with brief_fit_run, which shares the schedule arithmetic."""
+    n, batch, steps, ms = 2, 3000, 7, [3, 5]
     a, keep_a = _small_group(prec, n, batch=batch)
     b, keep_b = _small_group(prec, n, batch=batch)
     n_vox = 24 * 40 * 40
     gen = torch.Generator().manual_seed(1)
     idx = [torch.empty(n * batch, dtype=torch.int64).pin_memory() for _ in range(2)]
     loss = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(2)]
-    lr = 1e-3
     for s in range(steps):
         k = s & 1
         torch.cuda.synchronize()
@@ -53,16 +54,29 @@ def test_graphed_host_step_equals_separate_launches(prec, host_indices):
             idx[k].copy_(torch.randint(0, n_vox, (n * batch,), generator=gen))
         a.fit_step_host(idx[k] if host_indices else None, loss[k], "Adamax", 1e-3, milestones=ms, gamma=0.2, seed=42)
         want = b.fit_step(idx[k].cuda() if host_indices else None, seed=42, step=s)
-        cur = lr
+        cur = 1e-3
         for m in ms:
             if m <= s:
                 cur *= 0.2
         b.opt_step("Adamax", cur)
         torch.cuda.synchronize()
-        np.testing.assert_array_equal(loss[k].numpy(), want.cpu().numpy())
+        if s < ms[0]:  # same learning rate so far: the same loss and parameters to the bit
+            np.testing.assert_array_equal(loss[k].numpy(), want.cpu().numpy())
+            for j in range(n):
+                np.testing.assert_array_equal(a.get_params(j), b.get_params(j))
+        else:
+            np.testing.assert_allclose(loss[k].numpy(), want.cpu().numpy(), rtol=1e-5)
     for j in range(n):
-        np.testing.assert_array_equal(a.get_params(j), b.get_params(j))
+        np.testing.assert_allclose(a.get_params(j), b.get_params(j), rtol=1e-4, atol=1e-7)
     assert a.steps_done == steps
+    if not host_indices:
+        c, keep_c = _small_group(prec, n, batch=batch)
+        hist = c.fit_run(steps, "Adamax", 1e-3, milestones=ms, gamma=0.2, seed=42, loss_history=True)
+        torch.cuda.synchronize()
+        for j in range(n):
+            np.testing.assert_array_equal(a.get_params(j), c.get_params(j))
+        np.testing.assert_array_equal(hist[-1].cpu().numpy(), loss[(steps - 1) & 1].numpy())
+        c.close()
     a.close(); b.close()
 
 
