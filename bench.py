@@ -77,7 +77,7 @@ NAMED = {
     "neuron1024_nb4": dict(kind="neuron", shape=(1024, 1024, 1024), ratio=512, nb=4, alloc="by_size", thres=100, layers=7, w0=10.0,
                            rules=[(10001, 65535, 0.1)], fit=True,
                            desc="DivideTask neuron.yaml AS SHIPPED (Nb=4) on a synthetic 1024^3 u16 volume: 4 blocks 1024x512x512, "
-                                "SIREN L=7 f=228 (F_PAD > 128: fp32 CUDA-core fit kernels), randompoint batch 100000/block, Adamax"),
+                                "SIREN L=7 f=228 (F_PAD = 240: layer-wise tcgen05 kernels), randompoint batch 100000/block, Adamax"),
     "hipct2048": dict(kind="hipct", shape=(2048, 2048, 2048), ratio=128, nb=512, alloc="by_var", thres=26, layers=7, w0=10.0,
                       rules=[(65535, 65535, 1.0)], fit=True,
                       desc="DivideTask hipct.yaml on a synthetic 2048^3 u16 volume, ratio 128, Nb=512 -> 512 blocks 256^3, by_var "
@@ -883,6 +883,30 @@ def main():
     ggrp.close()
     del gvol, gidx
 
+    # ---- deblocking post-filter (deblock.cpp:226-321) on a decoded 512^3 uint16 volume cut into 8x8x8 = 512 blocks ----
+    deblock_stats = None
+    if world == 1 and not args.no_side_legs:
+        from brief_pytorch_b200.deblock import deblock_, seam_masks
+        dvol = torch.empty((512, 512, 512), dtype=torch.int16, device=dev)
+        dvol.random_(0, 30000)
+        names = [f"d_{z}_{z + 63}-h_{y}_{y + 63}-w_{x}_{x + 63}" for z in range(0, 512, 64) for y in range(0, 512, 64) for x in range(0, 512, 64)]
+        masks = seam_masks(names)
+        seam_px = sum(64 * 64 * bin(m & 15).count("1") for m in masks)  # 64 slices x 64 pixels per listed seam of a block
+        deblock_(dvol, names)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            deblock_(dvol, names)
+        torch.cuda.synchronize()
+        t_db = (time.perf_counter() - t0) / 3
+        deblock_stats = {"ms": 1e3 * t_db, "blocks": len(names), "seam_pixels": seam_px, "seam_pixels_per_s": seam_px / t_db,
+                         "gbs": seam_px * 20 / t_db / 1e9, "hbm_frac": seam_px * 20 / t_db / 1e9 / pk["hbm_gbs"],
+                         "note": "brief_deblock on a 512^3 uint16 volume, 512 blocks of 64^3 in the reference's listing order; "
+                                 "algorithmic bytes = 12 B read + 8 B written per seam pixel (6-tap read, 4-tap write); the launch is "
+                                 "bound by the reference's seam ORDER (seams cross and are filtered in place: one CTA per z slice "
+                                 "walks its seams with a barrier between them), not by HBM"}
+        del dvol
+
     # ---- NCCL, after the hot path: decoded blocks -> rank 0 (variable-size send/recv), checked by a checksum table ----
     gather = None
     if world > 1:
@@ -989,6 +1013,8 @@ def main():
                                        "rank 0's figure; peak = " + pk["src"] + " copy bandwidth (read+write)"}
         line["sampler_gather"] = gather_stats
         line["preprocess"] = pre_stats
+        if deblock_stats is not None:
+            line["deblock"] = deblock_stats
         if gather is not None:
             line["gather_decoded_blocks"] = gather
         if workloads is not None:

@@ -326,6 +326,9 @@ __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
 #ifndef BRIEF_FIT_CPT_A64
 #define BRIEF_FIT_CPT_A64 2
 #endif
+#ifndef BRIEF_FIT_TWO_ISSUERS
+#define BRIEF_FIT_TWO_ISSUERS 1
+#endif
 template <int F>
 struct FitCfg {
   static constexpr int NC = F / 16;                       // 16-column chunks per row
@@ -336,7 +339,10 @@ struct FitCfg {
   static constexpr int CPT_B = F == 64 ? BRIEF_FIT_CPT_B64 : CPT_A;
   static constexpr int CG_A = NC / CPT_A, CG_B = NC / CPT_B;  // column groups per role
   static constexpr int GW_A = 4 * CG_A, GW_B = 4 * CG_B;      // warps per role
-  static constexpr int THREADS = (GW_A + GW_B) * 32 + 64;     // + MMA-issue warp + sampler warp
+  // Two MMA-issue warps (one per chain) where one CTA owns the SM: a forward batch then shares the tensor pipe with a
+  // backward batch in flight instead of queueing behind all of its contractions (the forward chain is the longer one)
+  static constexpr bool TWO_ISSUERS = BRIEF_FIT_TWO_ISSUERS && F >= 48;
+  static constexpr int THREADS = (GW_A + GW_B) * 32 + 64 + (TWO_ISSUERS ? 32 : 0);  // + MMA-issue warp(s) + sampler warp
   static constexpr int MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 3;  // must match tc_fit_ctas_per_sm()
 };
 
@@ -355,7 +361,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool mma_warp = warp == NW, sampler_warp = warp == NW + 1;
+  const bool mma_warp = warp == NW, sampler_warp = warp == NW + 1, fwd_issue_warp = C::TWO_ISSUERS && warp == NW + 2;
+  __shared__ volatile int s_bwd_progress;  // two issuers: (tile, batches issued) of the backward chain, for the ring rule
   const bool group_a = warp >= GW_B && warp < NW;
   const int gw = group_a ? warp - GW_B : warp;  // warp index inside the role
   const int CPT = group_a ? C::CPT_A : C::CPT_B, CG = group_a ? C::CG_A : C::CG_B;
@@ -370,6 +377,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   const int slice = blockIdx.x - a.work_prefix[wi];
   tc_load_net(sn, a.nets[net_id]);
   if (t == 0) {
+    s_bwd_progress = 0;
     mbar_init(&bar_w, 1);
     mbar_init(&bar_a, 1);
     mbar_init(&bar_b, 1);
@@ -455,7 +463,48 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
       mma_f16(d, make_desc(aX + parity * BLK, kActLBO, 128), make_desc(aW + (uint32_t)img_l0_off(F, NH), (F / 8) * 128, 128),
               idesc_f, 0);
     };
+    // backward batch ia of tile kA (the caller has seen its trigger)
+    auto issue_backward = [&]() {
+      tc_fence_after();
+      const int pa = kA & 1;
+      const bool accum = kA > 0;
+      if (elect_one()) {
+        if (ia < NH) {
+          const int l = NH - ia;
+          const uint32_t dzb = aDz + (uint32_t)(sbA ^ (ia & 1)) * BUF;  // dz_l
+          auto recompute = [&](int m) {  // theta_m -> Zb[(m + 1) & 1], read by backward stage m + 1
+            const uint32_t d = TZB + (uint32_t)((m + 1) & 1) * zb_stride;
+            if (m >= 1) issue_forward<F>(d, aRing + slot(pa, m - 1), aW + (uint32_t)(m - 1) * F * F * 2);
+            else layer0(d, pa);
+          };
+          if (!zb2 || l == NH) recompute(l - 1);
+          if (ts) issue_dx_ts<F>(TXB, TAD, aW + (uint32_t)(l - 1) * F * F * 2);
+          else issue_dx<F>(TXB, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
+          commit(&bar_a);
+          issue_dw<F>(acc_addr(l - 1), dzb, aRing + slot(pa, l - 1), accum);
+          if (l == NH) issue_dw<16>(acc_addr(NH + 1), aRing + slot(pa, NH), aDY, accum);
+          if (l == 1) commit(&bar_f1);  // dW_1 done: the buffer of dz_1 may take the next tile's dz_NH
+          if (zb2 && l >= 2) recompute(l - 2);  // next stage's theta, behind this stage's dW
+        } else {  // dW0 += dz_0^T [x_hi, 1, x_lo, ...]; completes the tile
+          issue_dw<16>(acc_addr(NH), aDz + (uint32_t)(sbA ^ (NH & 1)) * BUF, aX + pa * BLK, accum);
+          commit(&bar_f2[pa]);
+        }
+      }
+      __syncwarp();
+      if (++ia > NH) { ia = 0; ++kA; sbA ^= sb_flip; }
+    };
     TT(m_start);
+    if (C::TWO_ISSUERS) {
+      // this warp issues the backward chain only; the forward chain has its own issue warp (below)
+      while (kA < n_tiles) {
+        if (ia == 0) { mbar_wait(&bar_lb, ph_lb); ph_lb ^= 1; }
+        else { mbar_wait(&bar_ra, ph_ra); ph_ra ^= 1; }
+        TT(m0);
+        issue_backward();
+        if (lane == 0) s_bwd_progress = kA * 32 + ia;  // published AFTER the batch has been issued
+        { TT(m1); TACC(0, m1 - m0); TACC(1, 1); }
+      }
+    } else
     while (kA < n_tiles) {
       bool progressed = false;
       TT(m0);
@@ -468,33 +517,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         a_ready = true;
       }
       if (a_ready) {
-        tc_fence_after();
-        const int pa = kA & 1;
-        const bool accum = kA > 0;
-        if (elect_one()) {
-          if (ia < NH) {
-            const int l = NH - ia;
-            const uint32_t dzb = aDz + (uint32_t)(sbA ^ (ia & 1)) * BUF;  // dz_l
-            auto recompute = [&](int m) {  // theta_m -> Zb[(m + 1) & 1], read by backward stage m + 1
-              const uint32_t d = TZB + (uint32_t)((m + 1) & 1) * zb_stride;
-              if (m >= 1) issue_forward<F>(d, aRing + slot(pa, m - 1), aW + (uint32_t)(m - 1) * F * F * 2);
-              else layer0(d, pa);
-            };
-            if (!zb2 || l == NH) recompute(l - 1);
-            if (ts) issue_dx_ts<F>(TXB, TAD, aW + (uint32_t)(l - 1) * F * F * 2);
-            else issue_dx<F>(TXB, dzb, aW + (uint32_t)(l - 1) * F * F * 2);
-            commit(&bar_a);
-            issue_dw<F>(acc_addr(l - 1), dzb, aRing + slot(pa, l - 1), accum);
-            if (l == NH) issue_dw<16>(acc_addr(NH + 1), aRing + slot(pa, NH), aDY, accum);
-            if (l == 1) commit(&bar_f1);  // dW_1 done: the buffer of dz_1 may take the next tile's dz_NH
-            if (zb2 && l >= 2) recompute(l - 2);  // next stage's theta, behind this stage's dW
-          } else {  // dW0 += dz_0^T [x_hi, 1, x_lo, ...]; completes the tile
-            issue_dw<16>(acc_addr(NH), aDz + (uint32_t)(sbA ^ (NH & 1)) * BUF, aX + pa * BLK, accum);
-            commit(&bar_f2[pa]);
-          }
-        }
-        __syncwarp();
-        if (++ia > NH) { ia = 0; ++kA; sbA ^= sb_flip; }
+        issue_backward();
         progressed = true;
         { TT(m1); TACC(0, m1 - m0); TACC(1, 1); }
       }
@@ -528,6 +551,36 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
       if (!progressed) { TT(m4); TACC(4, m4 - m0); }
     }
     { TT(m_end); TACC(5, m_end - m_start); TACC(6, n_tiles); }
+  } else if (fwd_issue_warp) {
+    // ============================================ forward-chain issue warp (two issuers) =========================
+    constexpr uint32_t idesc_f = make_idesc(128, F, false, false);
+    uint32_t ph_rb = 0;
+    for (int kB = 0; kB < n_tiles; ++kB) {
+      const int pb = kB & 1;
+      for (int ib = 0; ib <= NH; ++ib) {
+        // ring safety: batch b only after backward batch b-2 of tile kB-1 has been issued (its trailing dW is the last
+        // reader of the slot that a_b overwrites; the rule keeps one whole backward batch of slack behind that reader)
+        if (ib >= 2 && kB >= 1) {
+          for (;;) {
+            const int pr = s_bwd_progress, pk = pr >> 5, pi = pr & 31;
+            if (pk >= kB || (pk == kB - 1 && pi >= ib - 1)) break;
+            __nanosleep(20);
+          }
+        }
+        mbar_wait(&bar_rb, ph_rb);
+        ph_rb ^= 1;
+        tc_fence_after();
+        if (elect_one()) {
+          if (ib == 0)
+            mma_f16(TZF, make_desc(aX + pb * BLK, kActLBO, 128), make_desc(aW + (uint32_t)img_l0_off(F, NH), (F / 8) * 128, 128),
+                    idesc_f, 0);
+          else if (ts) issue_forward_ts<F>(TZF, TAF, aW + (uint32_t)(ib - 1) * F * F * 2);
+          else issue_forward<F>(TZF, aRing + slot(pb, ib - 1), aW + (uint32_t)(ib - 1) * F * F * 2);
+          commit(&bar_b);
+        }
+        __syncwarp();
+      }
+    }
   } else if (sampler_warp) {
     // ============================================ sampler warp ==================================================
     // main.py:126-163 / whole-block cube for one tile, up to two tiles ahead of its use: index -> coordinates (axis
