@@ -1334,11 +1334,58 @@ int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width
   const float xa = (float)index_a;
   const float alpha = (float)(0.8 * (std::pow(2.0, (double)(xa / 6)) - 1));
   const float beta = (float)(0.5 * (double)(float)index_b - 7);
-  DeblockBlock* d = nullptr;
-  CU(cudaMalloc(&d, blocks.size() * sizeof(DeblockBlock)));
-  cudaError_t e = cudaMemcpyAsync(d, blocks.data(), blocks.size() * sizeof(DeblockBlock), cudaMemcpyHostToDevice, st);
+  // the reference's seam list in its order (block by block; left, right, down, up), minus the seams its border guard
+  // skips (deblock.cpp:283-286), then the wave of every seam: 1 + the highest wave among the EARLIER seams it conflicts
+  // with (overlapping z range, and one seam's written voxels inside the other's 6-tap footprint)
+  std::vector<DeblockSeam> seams;
+  for (const DeblockBlock& k : blocks)
+    for (int s = 0; s < 4; ++s) {
+      if (!((k.mask >> s) & 1)) continue;
+      const int l = s == 1 ? k.x2 : k.x1, r = s == 0 ? k.x1 : k.x2;
+      const int dn = s == 3 ? k.y2 : k.y1, up = s == 2 ? k.y1 : k.y2;
+      if (l == r && (l - 3 < 0 || l + 3 > width - 1)) continue;
+      else if (dn == up && (dn - 3 < 0 || dn + 3 > height - 1)) continue;
+      if (l != r && dn != up) continue;  // not a line (cannot happen for the four seams of a block)
+      seams.push_back(DeblockSeam{k.z1, k.z2, l, r, dn, up});
+    }
+  struct Rect { int x0, x1, y0, y1; };
+  auto rects = [](const DeblockSeam& q, Rect& rd, Rect& wr) {
+    if (q.l == q.r) { rd = {q.l - 3, q.l + 2, q.d, q.u}; wr = {q.l - 2, q.l + 1, q.d, q.u}; }
+    else { rd = {q.l, q.r, q.d - 3, q.d + 2}; wr = {q.l, q.r, q.d - 2, q.d + 1}; }
+  };
+  auto hit = [](const Rect& a, const Rect& b) { return a.x0 <= b.x1 && b.x0 <= a.x1 && a.y0 <= b.y1 && b.y0 <= a.y1; };
+  const size_t ns = seams.size();
+  std::vector<int> wave(ns, 0);
+  std::vector<Rect> rd(ns), wr(ns);
+  for (size_t i = 0; i < ns; ++i) rects(seams[i], rd[i], wr[i]);
+  int n_waves = 0;
+  for (size_t j = 0; j < ns; ++j) {
+    int w = 0;
+    for (size_t i = 0; i < j; ++i) {
+      if (wave[i] < w) continue;
+      if (seams[i].z1 > seams[j].z2 || seams[j].z1 > seams[i].z2) continue;
+      if (hit(wr[i], rd[j]) || hit(rd[i], wr[j])) w = wave[i] + 1;
+    }
+    wave[j] = w;
+    n_waves = std::max(n_waves, w + 1);
+  }
+  if (ns == 0) return 0;
+  std::vector<int> wave_off((size_t)n_waves + 1, 0);
+  for (size_t i = 0; i < ns; ++i) wave_off[(size_t)wave[i] + 1]++;
+  for (int w = 0; w < n_waves; ++w) wave_off[(size_t)w + 1] += wave_off[(size_t)w];
+  std::vector<DeblockSeam> sorted(ns);
+  {
+    std::vector<int> cur(wave_off.begin(), wave_off.end() - 1);
+    for (size_t i = 0; i < ns; ++i) sorted[(size_t)cur[(size_t)wave[i]]++] = seams[i];
+  }
+  unsigned char* d = nullptr;
+  const size_t seam_bytes = ns * sizeof(DeblockSeam), off_bytes = wave_off.size() * sizeof(int);
+  CU(cudaMalloc(&d, seam_bytes + off_bytes));
+  cudaError_t e = cudaMemcpyAsync(d, sorted.data(), seam_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + seam_bytes, wave_off.data(), off_bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess)
-    e = launch_deblock(reinterpret_cast<unsigned short*>(dev_volume), depth, height, width, d, n_blocks, alpha, beta, thres, st);
+    e = launch_deblock(reinterpret_cast<unsigned short*>(dev_volume), depth, height, width, reinterpret_cast<const DeblockSeam*>(d),
+                       reinterpret_cast<const int*>(d + seam_bytes), n_waves, alpha, beta, thres, st);
   if (e == cudaSuccess) { g_launches.fetch_add(1); e = cudaStreamSynchronize(st); }
   cudaFree(d);
   if (e != cudaSuccess) return fail(BRIEF_ERR_CUDA, "brief_deblock: %s", cudaGetErrorString(e));

@@ -5,10 +5,10 @@
 // (C truncating divisions, float clip, uint16 wrap-around of the float -> uint16 conversion, deblock.cpp:33-71), the seam
 // list with its sticky duplicate flags (:244-276, built on the host by brief_deblock) and — because seams are filtered IN
 // PLACE and cross each other — the reference's traversal ORDER: block by block, z by z, (left, right, down, up).
-// Seams of different z never touch the same voxel, so one CTA owns one z-slice and walks that slice's seams in the
-// reference's order, with a CTA barrier between seams; the pixels along one seam are independent (each reads and writes
-// only its own row / column) and are spread over the CTA's threads.  Integer / byte work: no tensor cores, the kernel is
-// latency-bound on the barrier chain (blocks x 4 seams per slice), not on HBM — the seams are a tiny fraction of the volume.
+// Seams of different z never touch the same voxel, so one CTA owns one z-slice; seams whose footprints do not touch are
+// independent, so the host turns the reference's order into waves of mutually independent seams (see deblock_kernel).
+// Integer / byte work: no tensor cores; algorithmic bytes 12 B read + 8 B written per seam pixel, a tiny fraction of the
+// volume, so the launch is bound by the few barriers per slice and the strided column accesses, not by HBM.
 #include "brief_kernels.h"
 
 namespace brief {
@@ -37,33 +37,34 @@ __device__ __forceinline__ void deblock_pixel(unsigned short* ptr, long long s, 
   ptr[s] = (unsigned short)(int)((float)q1 + dq1);
 }
 
-__global__ void __launch_bounds__(256) deblock_kernel(unsigned short* img, int D, int H, int W, const DeblockBlock* blocks,
-                                                      int n_blocks, float alpha, float beta, int thres) {
-  const int z = blockIdx.x;
+// One CTA per z slice.  The seams of the slice are filtered in WAVES: the host orders the reference's seam list and gives
+// every seam the wave 1 + max(wave of the earlier seams whose footprint it touches), so the seams of one wave read and
+// write disjoint voxels — any order inside a wave, and the reference's order between conflicting seams, give the
+// reference's bits.  One CTA barrier per wave (a regular 8 x 8 block grid needs a handful) instead of one per seam; inside a
+// wave every warp takes a seam and spreads its pixels over the lanes.
+__global__ void __launch_bounds__(256) deblock_kernel(unsigned short* img, int D, int H, int W, const DeblockSeam* seams,
+                                                      const int* wave_off, int n_waves, float alpha, float beta, int thres) {
+  const int z = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   unsigned short* slice = img + (long long)z * H * W;
-  for (int b = 0; b < n_blocks; ++b) {
-    const DeblockBlock k = blocks[b];
-    if (z < k.z1 || z > k.z2) continue;  // CTA-uniform
-    for (int s = 0; s < 4; ++s) {
-      if (!((k.mask >> s) & 1)) continue;
-      const int l = s == 1 ? k.x2 : k.x1, r = s == 0 ? k.x1 : k.x2;
-      const int d = s == 3 ? k.y2 : k.y1, u = s == 2 ? k.y1 : k.y2;
-      if (l == r && (l - 3 < 0 || l + 3 > W - 1)) continue;
-      else if (d == u && (d - 3 < 0 || d + 3 > H - 1)) continue;
-      if (l == r) {  // vertical seam at column l: rows d..u, taps along x
-        for (int y = d + threadIdx.x; y <= u; y += blockDim.x) deblock_pixel(slice + (long long)y * W + l, 1, alpha, beta, thres);
-      } else if (d == u) {  // horizontal seam at row d: columns l..r, taps along y
-        for (int x = l + threadIdx.x; x <= r; x += blockDim.x) deblock_pixel(slice + (long long)d * W + x, W, alpha, beta, thres);
+  for (int w = 0; w < n_waves; ++w) {
+    const int lo = wave_off[w], hi = wave_off[w + 1];
+    for (int i = lo + warp; i < hi; i += n_warps) {
+      const DeblockSeam k = seams[i];
+      if (z < k.z1 || z > k.z2) continue;
+      if (k.l == k.r) {  // vertical seam at column l: rows d..u, taps along x
+        for (int y = k.d + lane; y <= k.u; y += 32) deblock_pixel(slice + (long long)y * W + k.l, 1, alpha, beta, thres);
+      } else {           // horizontal seam at row d: columns l..r, taps along y
+        for (int x = k.l + lane; x <= k.r; x += 32) deblock_pixel(slice + (long long)k.d * W + x, W, alpha, beta, thres);
       }
-      __syncthreads();  // the next seam may read what this one wrote
     }
+    __syncthreads();  // the next wave may read what this one wrote
   }
 }
 
-cudaError_t launch_deblock(unsigned short* img, int D, int H, int W, const DeblockBlock* dev_blocks, int n_blocks,
-                           float alpha, float beta, int thres, cudaStream_t st) {
-  if (D < 1 || n_blocks < 1) return cudaSuccess;
-  deblock_kernel<<<D, 256, 0, st>>>(img, D, H, W, dev_blocks, n_blocks, alpha, beta, thres);
+cudaError_t launch_deblock(unsigned short* img, int D, int H, int W, const DeblockSeam* dev_seams, const int* dev_wave_off,
+                           int n_waves, float alpha, float beta, int thres, cudaStream_t st) {
+  if (D < 1 || n_waves < 1) return cudaSuccess;
+  deblock_kernel<<<D, 256, 0, st>>>(img, D, H, W, dev_seams, dev_wave_off, n_waves, alpha, beta, thres);
   return cudaGetLastError();
 }
 

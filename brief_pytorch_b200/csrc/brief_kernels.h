@@ -139,8 +139,9 @@ cudaError_t launch_histogram(const void* dev_raw, long long n, int dtype, unsign
 
 // brief_deblock.cu
 struct DeblockBlock { int z1, z2, y1, y2, x1, x2, mask; };  // inclusive ends; mask bit 0..3 = left, right, down, up seam listed
-cudaError_t launch_deblock(unsigned short* img, int D, int H, int W, const DeblockBlock* dev_blocks, int n_blocks,
-                           float alpha, float beta, int thres, cudaStream_t st);
+struct DeblockSeam { int z1, z2, l, r, d, u; };                // one listed seam: columns l..r, rows d..u of slices z1..z2
+cudaError_t launch_deblock(unsigned short* img, int D, int H, int W, const DeblockSeam* dev_seams, const int* dev_wave_off,
+                           int n_waves, float alpha, float beta, int thres, cudaStream_t st);
 
 // brief_quality.cu
 cudaError_t launch_quality(const void* a, const void* b, int dtype, int D, int H, int W, const float* win11, float c1, float c2,

@@ -329,6 +329,9 @@ __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
 #ifndef BRIEF_FIT_TWO_ISSUERS
 #define BRIEF_FIT_TWO_ISSUERS 1
 #endif
+#ifndef BRIEF_FIT_TWO_ISSUERS_MIN_F
+#define BRIEF_FIT_TWO_ISSUERS_MIN_F 32
+#endif
 template <int F>
 struct FitCfg {
   static constexpr int NC = F / 16;                       // 16-column chunks per row
@@ -341,7 +344,7 @@ struct FitCfg {
   static constexpr int GW_A = 4 * CG_A, GW_B = 4 * CG_B;      // warps per role
   // Two MMA-issue warps (one per chain) where one CTA owns the SM: a forward batch then shares the tensor pipe with a
   // backward batch in flight instead of queueing behind all of its contractions (the forward chain is the longer one)
-  static constexpr bool TWO_ISSUERS = BRIEF_FIT_TWO_ISSUERS && F >= 48;
+  static constexpr bool TWO_ISSUERS = BRIEF_FIT_TWO_ISSUERS && F >= BRIEF_FIT_TWO_ISSUERS_MIN_F;
   static constexpr int THREADS = (GW_A + GW_B) * 32 + 64 + (TWO_ISSUERS ? 32 : 0);  // + MMA-issue warp(s) + sampler warp
   static constexpr int MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 3;  // must match tc_fit_ctas_per_sm()
 };

@@ -27,7 +27,15 @@ l.brief_debug_read_timing.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes
 l.brief_debug_read_timing(buf, 1)
 n_runs = 10
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); grp.fit_run(n_runs); e1.record()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if "--flush" in sys.argv else None
+e0.record()
+if flush is None:
+    grp.fit_run(n_runs)
+else:  # cold L2 before every step, like bench.py's `value`
+    for i in range(n_runs):
+        flush.fill_(i)
+        grp.fit_run(1)
+e1.record()
 torch.cuda.synchronize()
 print(f"f={f} L={L} batch={batch} nets={nets}: {e0.elapsed_time(e1) / n_runs * 1e3:.1f} us per step (instrumented build)")
 l.brief_debug_read_timing(buf, 0)
