@@ -3,6 +3,7 @@
 // No torch types cross this boundary; no CPU compute path exists behind it.
 #include <algorithm>
 #include <array>
+#include <map>
 #include <set>
 #include <atomic>
 #include <cmath>
@@ -11,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/brief_b200.h"
@@ -1305,7 +1307,15 @@ int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width
   // seam list (deblock.cpp:244-276): a block lists its left / right / down / up seam for every z of its range unless
   // the seam's flag is up; a flag goes up when the block's seam at z1 is already listed and never comes down again
   std::vector<DeblockBlock> blocks((size_t)n_blocks);
-  std::set<std::array<int, 5>> seen;
+  // listed seams: (l, r, d, u) -> z ranges (a seam is listed for every z of its block: ranges instead of one key per z)
+  std::map<std::array<int, 4>, std::vector<std::pair<int, int>>> seen;
+  auto listed = [&](const int* c, int z) {
+    auto it = seen.find({c[0], c[1], c[2], c[3]});
+    if (it == seen.end()) return false;
+    for (const auto& zr : it->second)
+      if (z >= zr.first && z <= zr.second) return true;
+    return false;
+  };
   bool flags[4] = {false, false, false, false};
   for (int i = 0; i < n_blocks; ++i) {
     const int32_t* b = host_blocks + 6 * (size_t)i;
@@ -1315,11 +1325,11 @@ int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width
       return fail(BRIEF_ERR_INVALID, "brief_deblock: block %d out of range", i);
     const int cand[4][4] = {{k.x1, k.x1, k.y1, k.y2}, {k.x2, k.x2, k.y1, k.y2}, {k.x1, k.x2, k.y1, k.y1}, {k.x1, k.x2, k.y2, k.y2}};
     for (int s = 0; s < 4; ++s)
-      if (seen.count({k.z1, cand[s][0], cand[s][1], cand[s][2], cand[s][3]})) flags[s] = true;
+      if (listed(cand[s], k.z1)) flags[s] = true;
     for (int s = 0; s < 4; ++s) {
       if (flags[s]) continue;
       k.mask |= 1 << s;
-      for (int z = k.z1; z <= k.z2; ++z) seen.insert({z, cand[s][0], cand[s][1], cand[s][2], cand[s][3]});
+      seen[{cand[s][0], cand[s][1], cand[s][2], cand[s][3]}].push_back({k.z1, k.z2});
     }
     blocks[(size_t)i] = k;
     if (host_masks) host_masks[i] = k.mask;
@@ -1359,15 +1369,31 @@ int brief_deblock(void* dev_volume, int32_t depth, int32_t height, int32_t width
   std::vector<Rect> rd(ns), wr(ns);
   for (size_t i = 0; i < ns; ++i) rects(seams[i], rd[i], wr[i]);
   int n_waves = 0;
-  for (size_t j = 0; j < ns; ++j) {
-    int w = 0;
-    for (size_t i = 0; i < j; ++i) {
-      if (wave[i] < w) continue;
-      if (seams[i].z1 > seams[j].z2 || seams[j].z1 > seams[i].z2) continue;
-      if (hit(wr[i], rd[j]) || hit(rd[i], wr[j])) w = wave[i] + 1;
+  {
+    // candidates through a coarse xy grid (64 x 64 voxel cells): a seam is compared only with the earlier seams that
+    // registered in a cell its own footprint touches
+    constexpr int kCell = 64;
+    std::unordered_map<long long, std::vector<int>> cells;
+    std::vector<int> stamp(ns, -1);
+    for (size_t j = 0; j < ns; ++j) {
+      int w = 0;
+      const int cx0 = std::max(rd[j].x0, 0) / kCell, cx1 = std::max(rd[j].x1, 0) / kCell;
+      const int cy0 = std::max(rd[j].y0, 0) / kCell, cy1 = std::max(rd[j].y1, 0) / kCell;
+      for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) {
+          auto& lst = cells[((long long)cy << 32) | (unsigned int)cx];
+          for (int i : lst) {
+            if (stamp[(size_t)i] == (int)j) continue;  // already compared through another cell
+            stamp[(size_t)i] = (int)j;
+            if (wave[(size_t)i] < w) continue;
+            if (seams[(size_t)i].z1 > seams[j].z2 || seams[j].z1 > seams[(size_t)i].z2) continue;
+            if (hit(wr[(size_t)i], rd[j]) || hit(rd[(size_t)i], wr[j])) w = wave[(size_t)i] + 1;
+          }
+          lst.push_back((int)j);
+        }
+      wave[j] = w;
+      n_waves = std::max(n_waves, w + 1);
     }
-    wave[j] = w;
-    n_waves = std::max(n_waves, w + 1);
   }
   if (ns == 0) return 0;
   std::vector<int> wave_off((size_t)n_waves + 1, 0);

@@ -34,6 +34,10 @@
 // 64 < F_PAD <= 128 fit on the wide kernel of brief_tc_wide.cu (streamed weights, stashed activations).
 #include "brief_tc_common.cuh"
 
+#ifndef BRIEF_PAD_SKIP
+#define BRIEF_PAD_SKIP 0  // experiment: no MUFU on the bias / pad columns of the boundary chunk (forward epilogues)
+#endif
+
 namespace brief {
 
 using namespace umma;
@@ -216,8 +220,12 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
               for (int i = 0; i < 16; ++i)
                 if (16 * c + i < n.f) zdump[16 * c + i] = vc[i] * inv;
             }
+#if BRIEF_PAD_SKIP
+            sin_chunk16_g4(vc, 16 * c, n.f);
+#else
 #pragma unroll
             for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
+#endif
             store_chunk16(sAct, r, c, vc);
           }
           signal(u);
@@ -663,8 +671,12 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           tmem_ld_wait();
           if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
+#if BRIEF_PAD_SKIP
+          sin_chunk16_g4(vc, 16 * (c_base + c), f);
+#else
 #pragma unroll
           for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
+#endif
           store_chunk16_both<false>(dst, r, c_base + c, vc, ts && st < NH, my_af + 8 * c);
           if (st == NH) {
 #pragma unroll

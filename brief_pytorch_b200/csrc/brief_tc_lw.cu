@@ -246,15 +246,21 @@ __global__ void __launch_bounds__(kLwThreads, 1) lw_gemm_kernel(LwArgs a) {
     for (int tile = c0; tile < n_tiles; tile += C, ++tl) {
       const int acc = tl & 1;
       const size_t toff = (size_t)(tbase + tile) * TB;
+      // BWD: this row's cosines of the layer below (up to 8 chunks of 32 bytes per thread) are fetched BEFORE the wait for
+      // the accumulator, all loads in flight together: their DRAM latency sits under the tile's contractions
+      uint4 kc[MODE == 2 ? 16 : 1];
+      if (MODE == 2) {
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+          if (c_lo + ci < c_hi) {
+            kc[2 * ci] = __ldcs(reinterpret_cast<const uint4*>(cin + toff + chunk_off(r, 2 * (c_lo + ci), kTile)));
+            kc[2 * ci + 1] = __ldcs(reinterpret_cast<const uint4*>(cin + toff + chunk_off(r, 2 * (c_lo + ci) + 1, kTile)));
+          }
+      }
       mbar_wait(&bar_accf[acc], (uint32_t)(tl >> 1) & 1);
       tc_fence_after();
-      for (int c = c_lo; c < c_hi; ++c) {
+      auto chunk = [&](int c, uint4 k0, uint4 k1) {
         float v[16];
-        uint4 k0, k1;
-        if (MODE == 2) {
-          k0 = *reinterpret_cast<const uint4*>(cin + toff + chunk_off(r, 2 * c, kTile));
-          k1 = *reinterpret_cast<const uint4*>(cin + toff + chunk_off(r, 2 * c + 1, kTile));
-        }
         tmem_ld16(tm + lane_base + (uint32_t)acc * 256 + 16 * c, v);
         tmem_ld_wait();
         if (MODE == 2) {
@@ -303,6 +309,13 @@ __global__ void __launch_bounds__(kLwThreads, 1) lw_gemm_kernel(LwArgs a) {
             *reinterpret_cast<uint4*>(out1 + toff + chunk_off(r, 2 * c + 1, kTile)) = make_uint4(w[4], w[5], w[6], w[7]);
           }
         }
+      };
+      if (MODE == 2) {
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci)
+          if (c_lo + ci < c_hi) chunk(c_lo + ci, kc[2 * ci], kc[2 * ci + 1]);
+      } else {
+        for (int c = c_lo; c < c_hi; ++c) chunk(c, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0));
       }
       tc_fence_before();
       __syncwarp();
