@@ -34,10 +34,6 @@
 // 64 < F_PAD <= 128 fit on the wide kernel of brief_tc_wide.cu (streamed weights, stashed activations).
 #include "brief_tc_common.cuh"
 
-#ifndef BRIEF_PAD_SKIP
-#define BRIEF_PAD_SKIP 0  // experiment: no MUFU on the bias / pad columns of the boundary chunk (forward epilogues)
-#endif
-
 namespace brief {
 
 using namespace umma;
@@ -220,12 +216,8 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
               for (int i = 0; i < 16; ++i)
                 if (16 * c + i < n.f) zdump[16 * c + i] = vc[i] * inv;
             }
-#if BRIEF_PAD_SKIP
-            sin_chunk16_g4(vc, 16 * c, n.f);
-#else
 #pragma unroll
             for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
-#endif
             store_chunk16(sAct, r, c, vc);
           }
           signal(u);
@@ -337,6 +329,9 @@ __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
 #ifndef BRIEF_FIT_TWO_ISSUERS
 #define BRIEF_FIT_TWO_ISSUERS 1
 #endif
+#ifndef BRIEF_FIT_TWO_SAMPLERS
+#define BRIEF_FIT_TWO_SAMPLERS 1
+#endif
 #ifndef BRIEF_FIT_TWO_ISSUERS_MIN_F
 #define BRIEF_FIT_TWO_ISSUERS_MIN_F 32
 #endif
@@ -353,7 +348,9 @@ struct FitCfg {
   // Two MMA-issue warps (one per chain) where one CTA owns the SM: a forward batch then shares the tensor pipe with a
   // backward batch in flight instead of queueing behind all of its contractions (the forward chain is the longer one)
   static constexpr bool TWO_ISSUERS = BRIEF_FIT_TWO_ISSUERS && F >= BRIEF_FIT_TWO_ISSUERS_MIN_F;
-  static constexpr int THREADS = (GW_A + GW_B) * 32 + 64 + (TWO_ISSUERS ? 32 : 0);  // + MMA-issue warp(s) + sampler warp
+  // ... and two sampler warps (two rows per lane each instead of four): the index -> voxel chain of a tile is half as long
+  static constexpr int SAMPLERS = (BRIEF_FIT_TWO_SAMPLERS && TWO_ISSUERS) ? 2 : 1;
+  static constexpr int THREADS = (GW_A + GW_B) * 32 + 64 + (TWO_ISSUERS ? 32 : 0) + (SAMPLERS - 1) * 32;  // + issue + sampler warps
   static constexpr int MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 3;  // must match tc_fit_ctas_per_sm()
 };
 
@@ -372,7 +369,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const bool mma_warp = warp == NW, sampler_warp = warp == NW + 1, fwd_issue_warp = C::TWO_ISSUERS && warp == NW + 2;
+  const bool mma_warp = warp == NW, fwd_issue_warp = C::TWO_ISSUERS && warp == NW + 2;
+  const bool sampler_warp = warp == NW + 1 || (C::SAMPLERS == 2 && warp == NW + 3);
   __shared__ volatile int s_bwd_progress;  // two issuers: (tile, batches issued) of the backward chain, for the ring rule
   const bool group_a = warp >= GW_B && warp < NW;
   const int gw = group_a ? warp - GW_B : warp;  // warp index inside the role
@@ -401,7 +399,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     // and a parity wait cannot tell a phase from the one two completions later
     mbar_init(&bar_lb, GW_B);
     for (int k = 0; k < 2; ++k) {
-      mbar_init(&bar_gfull[k], 1);    // sampler warp: staging slot k holds a tile's samples
+      mbar_init(&bar_gfull[k], C::SAMPLERS);  // sampler warp(s): staging slot k holds a tile's samples
       mbar_init(&bar_gfree[k], GW_B);   // group B: staging slot k has been consumed
     }
     fence_mbar_init();
@@ -596,16 +594,18 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     // ============================================ sampler warp ==================================================
     // main.py:126-163 / whole-block cube for one tile, up to two tiles ahead of its use: index -> coordinates (axis
     // tables), raw voxel -> normalised target, loss weight; 4 rows per lane
+    constexpr int SR = 4 / C::SAMPLERS;                 // rows per lane of this warp
+    const int h0 = (warp == NW + 1) ? 0 : SR;             // first 32-row group of this warp
     for (int k = 0; k < n_tiles; ++k) {
       const int sl = k & 1;
       if (k >= 2) mbar_wait(&bar_gfree[sl], (uint32_t)((k >> 1) - 1) & 1);
-      // three passes so that the four rows' dependent loads (index -> voxel, index -> axis tables) are all in flight
+      // three passes so that the rows' dependent loads (index -> voxel, index -> axis tables) are all in flight
       // together instead of one row's chain after the other (rows past the slice end read voxel 0 and are zeroed)
-      long long idx[4];
-      bool ok[4];
+      long long idx[SR];
+      bool ok[SR];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const long long s = s_begin + (long long)k * kTile + lane + 32 * h;
+      for (int h = 0; h < SR; ++h) {
+        const long long s = s_begin + (long long)k * kTile + lane + 32 * (h0 + h);
         ok[h] = s < s_end;
         long long v = 0;
         if (ok[h]) {
@@ -615,15 +615,15 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         }
         idx[h] = v;
       }
-      float raw[4], cx[4][3];
+      float raw[SR], cx[SR][3];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
+      for (int h = 0; h < SR; ++h) {
         raw[h] = brief_raw_value(n, idx[h]);
         brief_coords(n, a.axes, idx[h], cx[h][0], cx[h][1], cx[h][2]);
       }
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int row = lane + 32 * h;
+      for (int h = 0; h < SR; ++h) {
+        const int row = lane + 32 * (h0 + h);
         const float yv = ok[h] ? brief_normalize(n, raw[h]) : 0.f;
         const float wv = ok[h] ? brief_weight(n, idx[h], raw[h]) : 0.f;
         s_g[sl][row] = ok[h] ? make_float4(cx[h][0], cx[h][1], cx[h][2], yv) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -671,12 +671,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
           tmem_ld_wait();
           if (c + 1 < C::CPT_B) tmem_ld16(my_tmem + 16 * (c + 1), v[(c + 1) & 1]);
           float* vc = v[c & 1];
-#if BRIEF_PAD_SKIP
-          sin_chunk16_g4(vc, 16 * (c_base + c), f);
-#else
 #pragma unroll
           for (int i = 0; i < 16; ++i) vc[i] = fast_sin(vc[i]);
-#endif
           store_chunk16_both<false>(dst, r, c_base + c, vc, ts && st < NH, my_af + 8 * c);
           if (st == NH) {
 #pragma unroll

@@ -76,30 +76,6 @@ __device__ __forceinline__ void sin_chunk16(float* v, int col0, int f) {
   }
 }
 
-// The same with warp-uniform branches per group of FOUR columns (f is CTA-uniform): whole groups of real columns keep the
-// plain FMUL / MUFU sequence, groups beyond the bias columns are skipped, and at most one group per row is mixed.
-__device__ __forceinline__ void sin_chunk16_g4(float* v, int col0, int f) {
-  if (col0 + 16 <= f) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fast_sin(v[i]);
-    return;
-  }
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int c = col0 + 4 * g;
-    if (c + 4 <= f) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[4 * g + i] = fast_sin(v[4 * g + i]);
-    } else if (c >= f + 2) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[4 * g + i] = 0.0f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[4 * g + i] = c + i < f ? fast_sin(v[4 * g + i]) : (c + i < f + 2 ? 1.0f : 0.0f);
-    }
-  }
-}
-
 // dz = dX * scale * cos(theta) for one 16-column chunk; columns >= f (bias columns: cos(pi/2), pads: dX = 0) are zero
 __device__ __forceinline__ void cos_mul_chunk16(float* z, const float* x, float scale, int col0, int f) {
   if (col0 + 16 <= f) {
