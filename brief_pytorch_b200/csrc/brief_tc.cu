@@ -329,6 +329,9 @@ __host__ __device__ constexpr int fit_tmem_cols(int F, int NH) {
 #ifndef BRIEF_FIT_TWO_ISSUERS
 #define BRIEF_FIT_TWO_ISSUERS 1
 #endif
+#ifndef BRIEF_FIT_DZ_IN_A
+#define BRIEF_FIT_DZ_IN_A 1
+#endif
 #ifndef BRIEF_FIT_TWO_SAMPLERS
 #define BRIEF_FIT_TWO_SAMPLERS 1
 #endif
@@ -350,6 +353,9 @@ struct FitCfg {
   static constexpr bool TWO_ISSUERS = BRIEF_FIT_TWO_ISSUERS && F >= BRIEF_FIT_TWO_ISSUERS_MIN_F;
   // ... and two sampler warps (two rows per lane each instead of four): the index -> voxel chain of a tile is half as long
   static constexpr int SAMPLERS = (BRIEF_FIT_TWO_SAMPLERS && TWO_ISSUERS) ? 2 : 1;
+  // dz_NH = (w_h dy') Wlast cos(theta_NH) formed by the BACKWARD group (whose chain is the shorter one) instead of the
+  // forward group's loss phase; only with two issuers (the single-issuer schedule keeps the loss hand-over it was tuned with)
+  static constexpr bool DZ_IN_A = BRIEF_FIT_DZ_IN_A && TWO_ISSUERS;
   static constexpr int THREADS = (GW_A + GW_B) * 32 + 64 + (TWO_ISSUERS ? 32 : 0) + (SAMPLERS - 1) * 32;  // + issue + sampler warps
   static constexpr int MIN_BLOCKS = F >= 48 ? 1 : F == 32 ? 2 : 3;  // must match tc_fit_ctas_per_sm()
 };
@@ -361,11 +367,12 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
   constexpr int NW = GW_A + GW_B;  // epilogue warps: [0, GW_B) group B (forward), [GW_B, NW) group A (backward)
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_lb, bar_f1, bar_f2[2], bar_gfull[2], bar_gfree[2];
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_b, bar_ra, bar_rb, bar_lb, bar_zf, bar_f1, bar_f2[2], bar_gfull[2], bar_gfree[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float4 s_g[2][kTile];  // sampler staging: (x0, x1, x2, normalised target) per row
   __shared__ float s_gw[2][kTile];                //                  loss weight per row
   __shared__ float s_y[CG_B][kTile];
+  __shared__ float s_dys[C::DZ_IN_A ? 2 : 1][C::DZ_IN_A ? kTile : 1];  // w_h dy' per row: loss phase (group B) -> dz_NH stage (group A)
   __shared__ float s_red[4];
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -398,6 +405,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     // "loss phase done" has its own barrier: group B raises it and the NEXT tile's first bar_rb signal back to back,
     // and a parity wait cannot tell a phase from the one two completions later
     mbar_init(&bar_lb, GW_B);
+    mbar_init(&bar_zf, GW_A);  // DZ_IN_A: group A has read theta_NH out of Zf (the next tile's layer-0 contraction may overwrite it)
     for (int k = 0; k < 2; ++k) {
       mbar_init(&bar_gfull[k], C::SAMPLERS);  // sampler warp(s): staging slot k holds a tile's samples
       mbar_init(&bar_gfree[k], GW_B);   // group B: staging slot k has been consumed
@@ -506,8 +514,8 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     if (C::TWO_ISSUERS) {
       // this warp issues the backward chain only; the forward chain has its own issue warp (below)
       while (kA < n_tiles) {
-        if (ia == 0) { mbar_wait(&bar_lb, ph_lb); ph_lb ^= 1; }
-        else { mbar_wait(&bar_ra, ph_ra); ph_ra ^= 1; }
+        if (ia == 0 && !C::DZ_IN_A) { mbar_wait(&bar_lb, ph_lb); ph_lb ^= 1; }  // loss done: dz_NH in place
+        else { mbar_wait(&bar_ra, ph_ra); ph_ra ^= 1; }                         // group A wrote dz_l (DZ_IN_A: also dz_NH)
         TT(m0);
         issue_backward();
         if (lane == 0) s_bwd_progress = kA * 32 + ia;  // published AFTER the batch has been issued
@@ -578,6 +586,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         }
         mbar_wait(&bar_rb, ph_rb);
         ph_rb ^= 1;
+        if (C::DZ_IN_A && ib == 0 && kB >= 1) mbar_wait(&bar_zf, (uint32_t)(kB - 1) & 1);  // theta_NH of tile kB-1 consumed
         tc_fence_after();
         if (elect_one()) {
           if (ib == 0)
@@ -716,7 +725,9 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
       TACC(4, b7 - b6); TACC(5, b8 - b7);
       if (cg == 0) *reinterpret_cast<uint4*>(sDY + chunk_off(r, 0, kTile)) = make_uint4(pack_f16x2_sat(dys, 0.f), 0, 0, 0);
       dys *= wh;
-      {
+      if (C::DZ_IN_A) {
+        if (cg == 0) s_dys[p][r] = dys;  // group A forms dz_NH from this and theta_NH (still in Zf)
+      } else {
         unsigned char* dzb = sDz + (size_t)sb * BUF;
         float v[2][16];
         tmem_ld16(my_tmem, v[0]);  // theta_NH is still in Zf: the next forward MMA is issued after this signal
@@ -746,6 +757,36 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
     const float w0_over_wh = w0 / wh;
     TT(a_start);
     for (int k = 0; k < n_tiles; ++k) {
+      if (C::DZ_IN_A) {  // dz_NH = (w_h dy') Wlast cos(theta_NH): theta_NH is still in Zf, dy' comes from group B's loss phase
+        TT(a0);
+        mbar_wait(&bar_lb, (uint32_t)k & 1);
+        if (k >= 1) mbar_wait(&bar_f1, (uint32_t)(k - 1) & 1);  // dW_1 of tile k-1 done: dz buffer sb is free
+        tc_fence_after();
+        TT(a1);
+        TACC(0, a1 - a0);
+        unsigned char* dzb = sDz + (size_t)sb * BUF;
+        const float dys = s_dys[k & 1][r];
+        float v[C::CPT_A][16];
+#pragma unroll
+        for (int c = 0; c < C::CPT_A; ++c) tmem_ld16(my_tmem + 16 * c, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_zf);  // Zf may be overwritten by the next tile's layer-0 contraction
+#pragma unroll
+        for (int c = 0; c < C::CPT_A; ++c) {
+          float* vc = v[c];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_wl + 16 * (c_base + c) + i);
+            vc[i] = dys * w4.x * fast_cos(vc[i]); vc[i + 1] = dys * w4.y * fast_cos(vc[i + 1]);
+            vc[i + 2] = dys * w4.z * fast_cos(vc[i + 2]); vc[i + 3] = dys * w4.w * fast_cos(vc[i + 3]);
+          }
+          store_chunk16_both<true>(dzb, r, c_base + c, vc, ts, my_ad + 8 * c);
+        }
+        signal(&bar_ra);
+        { TT(a2); TACC(4, a2 - a1); }
+      }
       for (int ia = 0; ia < NH; ++ia) {  // stage l = NH - ia: dz_{l-1} = dX_{l-1} * w * cos(theta_{l-1})
         const int l = NH - ia;
         TT(a0);
@@ -753,7 +794,7 @@ __global__ void __launch_bounds__(FitCfg<F>::THREADS, FitCfg<F>::MIN_BLOCKS) tc_
         ph_a ^= 1;
         tc_fence_after();
         TT(a1);
-        if (ia == 0) TACC(0, a1 - a0); else TACC(1, a1 - a0);
+        if (ia == 0 && !C::DZ_IN_A) TACC(0, a1 - a0); else TACC(1, a1 - a0);
         unsigned char* dzb = sDz + (size_t)(sb ^ ((ia + 1) & 1)) * BUF;  // dz_{l-1}
         const float scale = l >= 2 ? 1.0f : w0_over_wh;  // dX carries w_hidden (omega-scaled weights); layer 0 wants w_0
         float vz[2][16], vx[2][16];

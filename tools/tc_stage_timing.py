@@ -50,7 +50,7 @@ tb = max(1, v[8])
 show("group B (forward) warp 0", 0, ["wait f2 (tile k-2 done)", "wait sampler", f"wait MMA x{NH + 1}", f"sine epilogue x{NH + 1}",
                                     "y exchange + loss", "wait f1 (dz buffer free)", "dz_NH + signal", "TOTAL"], tb)
 ta = max(1, v[16 + 8])
-show("group A (backward) warp 0", 16, ["wait MMA (first stage of tile)", f"wait MMA x{NH - 1}", f"cos epilogue x{NH}", f"signal x{NH}", "", "", "", "TOTAL"], ta)
+show("group A (backward) warp 0", 16, ["wait loss done (+ dz buffer)", f"wait MMA x{NH}", f"cos epilogue x{NH}", f"signal x{NH}", "dz_NH stage", "", "", "TOTAL"], ta)
 print(f"per launch (warp 0): prologue {v[9] / n_runs:.0f} cyc, wait for the other roles at the end {v[10] / n_runs:.0f}, "
       f"gradient flush {v[11] / n_runs:.0f}, kernel total {v[12] / n_runs:.0f}")
 tm = max(1, v[32 + 6])
