@@ -59,8 +59,14 @@ constexpr int kEvalSlots = 2;
 constexpr int kEvalMaxUnits = kEvalMaxGroups * kEvalSlots;
 __host__ __device__ constexpr size_t eval_unit_bytes(int F) { return (size_t)kTile * F * 2 + (size_t)kTile * 16 * 2; }
 
+#ifndef BRIEF_EVAL_ISSUERS
+#define BRIEF_EVAL_ISSUERS 4  // MMA-issue warps of the decode kernel: issuer i serves the units of groups i, i + 4, ... in a fixed order
+#endif
+// F <= 32: two CTAs per SM, register-bound; F > 64: one or two units per CTA, nothing to interleave
+__host__ __device__ constexpr int eval_issuers(int F) { return (F <= 32 || F > 64) ? 1 : BRIEF_EVAL_ISSUERS; }
 template <int F, bool DUMP>
-__global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc_eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32 * eval_issuers(F), F <= 32 ? 2 : 1) tc_eval_kernel(EvalArgs a) {
+  constexpr int kEvalIssuers = eval_issuers(F);
   constexpr int NC = F / 16;  // 16-column chunks per row
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
@@ -68,8 +74,9 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
   __shared__ uint32_t tmem_base_s;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int G = (blockDim.x - 32) >> 7, S = a.eval_slots, U = G * S;  // S tile slots per group (2; 1 when F is wide)
-  const bool mma_warp = warp == 4 * G;
+  const int G = (blockDim.x - 32 * kEvalIssuers) >> 7, S = a.eval_slots, U = G * S;  // S tile slots per group (2; 1 when F is wide)
+  const bool mma_warp = warp >= 4 * G;
+  const int issuer = warp - 4 * G;  // which of the issue warps (mma_warp only)
   const int g = warp >> 2, q = warp & 3, r = 32 * q + lane;
   int net_id;
   long long chunk;
@@ -125,6 +132,7 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32, F <= 32 ? 2 : 1) tc
         for (int slot = 0; slot < S; ++slot)
           for (int gi = 0; gi < G; ++gi) {
             const int u = gi * S + slot;
+            if (kEvalIssuers > 1 && (gi % kEvalIssuers) != issuer) continue;  // the other issue warp's unit
             if (it * U + u >= count) continue;  // this unit has no tile in the last round
             mbar_wait(&bar_r[u], ph);
             tc_fence_after();
@@ -964,11 +972,11 @@ static cudaError_t launch_eval_f(const EvalArgs& a_in, int L_max, int n_blocks, 
   if (a.layers_out) {
     e = cudaFuncSetAttribute(tc_eval_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, true><<<n_blocks, G * 128 + 32, smem, st>>>(a);
+    tc_eval_kernel<F, true><<<n_blocks, G * 128 + 32 * eval_issuers(F), smem, st>>>(a);
   } else {
     e = cudaFuncSetAttribute(tc_eval_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, false><<<n_blocks, G * 128 + 32, smem, st>>>(a);
+    tc_eval_kernel<F, false><<<n_blocks, G * 128 + 32 * eval_issuers(F), smem, st>>>(a);
   }
   return cudaGetLastError();
 }
