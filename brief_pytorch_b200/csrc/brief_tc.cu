@@ -64,18 +64,30 @@ __host__ __device__ constexpr size_t eval_unit_bytes(int F) { return (size_t)kTi
 #endif
 // F <= 32: two CTAs per SM, register-bound; F > 64: one or two units per CTA, nothing to interleave
 __host__ __device__ constexpr int eval_issuers(int F) { return (F <= 32 || F > 64) ? 1 : BRIEF_EVAL_ISSUERS; }
+// Wide decode (F >= 112): the hidden weights do not stay resident (5 x 32 KB at F = 128 would leave room for ONE tile, i.e.
+// no overlap at all).  The units of a CTA walk the layers in lockstep anyway (fixed service order), so ONE layer's weights at
+// a time are enough: a producer warp streams W_1 .. W_NH, round after round, through two [F x F] buffers (bulk copies,
+// freed by tcgen05.commit), and the shared memory saved holds four tiles in flight instead of one.
+__host__ __device__ constexpr bool eval_streams(int F) { return F >= 112; }
+__host__ __device__ constexpr size_t eval_tail_bytes(int F, int NH) { return (img_bytes(F, NH) - img_l0_off(F, NH) + 127) & ~(size_t)127; }
+__host__ __device__ constexpr size_t eval_weight_bytes(int F, int NH) {  // shared memory in front of the tile units
+  return eval_streams(F) ? eval_tail_bytes(F, NH) + 2 * (size_t)F * F * 2 : img_bytes_padded(F, NH);
+}
 template <int F, bool DUMP>
-__global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32 * eval_issuers(F), F <= 32 ? 2 : 1) tc_eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32 * eval_issuers(F) + (eval_streams(F) ? 32 : 0), F <= 32 ? 2 : 1)
+    tc_eval_kernel(EvalArgs a) {
   constexpr int kEvalIssuers = eval_issuers(F);
+  constexpr bool STREAM = eval_streams(F);
   constexpr int NC = F / 16;  // 16-column chunks per row
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ NetDev sn;
-  __shared__ __align__(8) uint64_t bar_w, bar_mma[kEvalMaxUnits], bar_r[kEvalMaxUnits];
+  __shared__ __align__(8) uint64_t bar_w, bar_mma[kEvalMaxUnits], bar_r[kEvalMaxUnits], bar_wfull[2], bar_wfree[2];
   __shared__ uint32_t tmem_base_s;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int G = (blockDim.x - 32 * kEvalIssuers) >> 7, S = a.eval_slots, U = G * S;  // S tile slots per group (2; 1 when F is wide)
-  const bool mma_warp = warp >= 4 * G;
+  const int G = (blockDim.x - 32 * kEvalIssuers - (STREAM ? 32 : 0)) >> 7, S = a.eval_slots, U = G * S;  // S tile slots per group
+  const bool mma_warp = warp >= 4 * G && warp < 4 * G + kEvalIssuers;
+  const bool producer_warp = STREAM && warp == 4 * G + kEvalIssuers;
   const int issuer = warp - 4 * G;  // which of the issue warps (mma_warp only)
   const int g = warp >> 2, q = warp & 3, r = 32 * q + lane;
   int net_id;
@@ -96,6 +108,7 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32 * eval_issuers(F), F
       mbar_init(&bar_mma[i], 1);
       mbar_init(&bar_r[i], 4);  // "this unit's operand rows are written": one arrival per warp of the group
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wfree[i], 1); }
     fence_mbar_init();
   }
   const uint32_t tcols = (uint32_t)tmem_cols_pow2(U * F);
@@ -105,12 +118,14 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32 * eval_issuers(F), F
   tc_fence_after();
   const NetDev& n = sn;
   const int NH = n.L - 2;
-  unsigned char* sW = smem;  // packed image
-  unsigned char* sUnits = sW + img_bytes_padded(F, NH);  // per unit: [128 x F] activations | [128 x 16] layer-0 rows
+  // resident: the whole packed image, or (STREAM) its tail [layer-0 block | last block | side] followed by two weight buffers
+  unsigned char* sW = smem;
+  unsigned char* sWbuf = smem + eval_tail_bytes(F, NH);
+  unsigned char* sUnits = sW + eval_weight_bytes(F, NH);  // per unit: [128 x F] activations | [128 x 16] layer-0 rows
   if (t == 0) {
-    const uint32_t bytes = (uint32_t)img_bytes(F, NH);
+    const uint32_t bytes = (uint32_t)(STREAM ? img_bytes(F, NH) - img_l0_off(F, NH) : img_bytes(F, NH));
     mbar_expect_tx(&bar_w, bytes);
-    bulk_g2s(sW, a.wpack + n.wpack_off, bytes, &bar_w);
+    bulk_g2s(sW, a.wpack + n.wpack_off + (STREAM ? img_l0_off(F, NH) : 0), bytes, &bar_w);
   }
   const uint32_t tm = tmem_base_s;
   const long long total = a.coords ? a.n_coords : n.n_vox;
@@ -121,14 +136,34 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32 * eval_issuers(F), F
   mbar_wait(&bar_w, 0);
   __syncthreads();
 
-  if (mma_warp) {
+  if (producer_warp) {
+    // hidden weights in stream order: round after round W_1 .. W_NH into buffer (h & 1)
+    if (elect_one()) {
+      const int total_h = rounds * NH;
+      for (int h = 0; h < total_h; ++h) {
+        const int b = h & 1;
+        if (h >= 2) mbar_wait(&bar_wfree[b], (uint32_t)((h >> 1) - 1) & 1);
+        mbar_expect_tx(&bar_wfull[b], (uint32_t)F * F * 2);
+        bulk_g2s(sWbuf + (size_t)b * F * F * 2, a.wpack + n.wpack_off + (size_t)(h % NH) * F * F * 2, (uint32_t)F * F * 2, &bar_wfull[b]);
+      }
+    }
+    __syncwarp();
+  } else if (mma_warp) {
     const uint32_t aW = smem_u32(sW), aU0 = smem_u32(sUnits);
+    const uint32_t aL0 = aW + (STREAM ? 0u : (uint32_t)img_l0_off(F, NH));
+    const uint32_t aLast = aL0 + (uint32_t)img_l0_bytes(F);
+    const uint32_t aWb = smem_u32(sWbuf);
     const int steps = NH + 2;  // MMA batches per tile
     uint32_t ph = 0;           // every active unit's barrier flips once per step: one shared parity
     constexpr uint32_t idesc_last = make_idesc(128, 16, false, false);
     constexpr uint32_t idesc_f = make_idesc(128, F, false, false);
     for (int it = 0; it < rounds; ++it)
       for (int st = 0; st < steps; ++st) {
+        const int hb = (it * NH + st - 1) & 1;  // STREAM: buffer of this hidden step's weights
+        if (STREAM && st >= 1 && st <= NH) {
+          mbar_wait(&bar_wfull[hb], (uint32_t)((it * NH + st - 1) >> 1) & 1);
+          tc_fence_after();
+        }
         for (int slot = 0; slot < S; ++slot)
           for (int gi = 0; gi < G; ++gi) {
             const int u = gi * S + slot;
@@ -140,20 +175,22 @@ __global__ void __launch_bounds__(kEvalMaxGroups * 128 + 32 * eval_issuers(F), F
               const uint32_t act = aU0 + (uint32_t)u * (uint32_t)eval_unit_bytes(F);
               const uint32_t d = tm + (uint32_t)u * F;
               if (st == 0) {  // theta_0 = A0 [128 x 16] * B0^T
-                mma_f16(d, make_desc(act + kTile * F * 2, kActLBO, 128),
-                        make_desc(aW + (uint32_t)img_l0_off(F, NH), (F / 8) * 128, 128), idesc_f, 0);
+                mma_f16(d, make_desc(act + kTile * F * 2, kActLBO, 128), make_desc(aL0, (F / 8) * 128, 128), idesc_f, 0);
               } else if (st <= NH) {
-                issue_forward<F>(d, act, aW + (uint32_t)(st - 1) * F * F * 2);
+                issue_forward<F>(d, act, STREAM ? aWb + (uint32_t)hb * F * F * 2 : aW + (uint32_t)(st - 1) * F * F * 2);
               } else {  // y = a_NH * [hi(Wlast); lo(Wlast)]^T  (N = 16)
 #pragma unroll
                 for (int k = 0; k < F / 16; ++k)
-                  mma_f16(d, make_desc(act + k * 2 * kActLBO, kActLBO, 128),
-                          make_desc(aW + (uint32_t)img_last_off(F, NH) + k * 2 * 256, 256, 128), idesc_last, k > 0);
+                  mma_f16(d, make_desc(act + k * 2 * kActLBO, kActLBO, 128), make_desc(aLast + k * 2 * 256, 256, 128), idesc_last, k > 0);
               }
               commit(&bar_mma[u]);
             }
             __syncwarp();
           }
+        if (STREAM && st >= 1 && st <= NH) {  // every contraction of this layer has been issued: its buffer is free once they complete
+          if (elect_one()) commit(&bar_wfree[hb]);
+          __syncwarp();
+        }
         ph ^= 1;
       }
   } else {
@@ -907,7 +944,7 @@ int tc_fpad(int f) { return ((f + 2 + 15) / 16) * 16; }  // two constant-one col
 size_t tc_wpack_bytes(int F, int L) { return img_bytes(F, L - 2); }
 // groups per CTA and tile slots per group: TMEM columns (G S F <= 512) and shared memory (image + G S unit buffers)
 static void eval_shape(int F, int L, int* groups, int* slots) {
-  const size_t img = img_bytes_padded(F, L - 2);
+  const size_t img = eval_weight_bytes(F, L - 2);
   const size_t budget = (F <= 32 ? (size_t)110 : (size_t)224) * 1024;  // F <= 32: two CTAs per SM
   *groups = 0;
   *slots = 0;
@@ -925,7 +962,7 @@ static void eval_shape(int F, int L, int* groups, int* slots) {
 int tc_eval_groups(int F, int L) { int g, s; eval_shape(F, L, &g, &s); return g; }
 int tc_eval_slots(int F, int L) { int g, s; eval_shape(F, L, &g, &s); return s; }
 size_t tc_eval_smem(int F, int L) {
-  return img_bytes_padded(F, L - 2) + (size_t)tc_eval_groups(F, L) * tc_eval_slots(F, L) * eval_unit_bytes(F);
+  return eval_weight_bytes(F, L - 2) + (size_t)tc_eval_groups(F, L) * tc_eval_slots(F, L) * eval_unit_bytes(F);
 }
 // forward / decompress on the tensor core: any width whose padded image + one tile fit (f <= 126 at L = 7)
 bool tc_eval_supported(int f, int L, int in_dim, int out_dim) {
@@ -972,11 +1009,11 @@ static cudaError_t launch_eval_f(const EvalArgs& a_in, int L_max, int n_blocks, 
   if (a.layers_out) {
     e = cudaFuncSetAttribute(tc_eval_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, true><<<n_blocks, G * 128 + 32 * eval_issuers(F), smem, st>>>(a);
+    tc_eval_kernel<F, true><<<n_blocks, G * 128 + 32 * eval_issuers(F) + (eval_streams(F) ? 32 : 0), smem, st>>>(a);
   } else {
     e = cudaFuncSetAttribute(tc_eval_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tc_eval_kernel<F, false><<<n_blocks, G * 128 + 32 * eval_issuers(F), smem, st>>>(a);
+    tc_eval_kernel<F, false><<<n_blocks, G * 128 + 32 * eval_issuers(F) + (eval_streams(F) ? 32 : 0), smem, st>>>(a);
   }
   return cudaGetLastError();
 }
