@@ -27,11 +27,13 @@
 // F >= f + 2); pad weights are zero.  Because columns f, f+1 of every activation buffer are the constant 1, the bias
 // gradients fall out of the dW contractions as column f.
 //
-// Decompress kernel: up to 4 groups x 2 alternating tile slots per CTA share one image (8 tiles in flight per SM);
-// bound by the special-function unit (XU pipe 76 %).  Fit kernel: two tiles in flight on separate warp groups (forward /
-// backward), event-driven MMA-issue warp, dW accumulated across the slice's tiles in TMEM; bound by a latency chain on
-// a tensor pipe whose N = 64 SS-mode contractions are operand-fetch-limited.  Networks with
-// 64 < F_PAD <= 128 fit on the wide kernel of brief_tc_wide.cu (streamed weights, stashed activations).
+// Decompress kernel: up to 4 groups x 2 alternating tile slots per CTA share one image (8 tiles in flight per SM), one
+// MMA-issue warp per group at F = 48 / 64; at F >= 112 the hidden weights are streamed layer by layer through two buffers
+// so that four tiles fit instead of one; bound by the special-function unit.  Fit kernel: two tiles in flight on separate
+// warp groups (forward / backward), ONE MMA-ISSUE WARP PER CHAIN and two sampler warps (F >= 32), dz_NH formed by the
+// backward group, dW accumulated across the slice's tiles in TMEM; bound by the sine / cosine epilogues of two chains on
+// one SFU.  Networks with 64 < F_PAD <= 128 fit on the wide kernel of brief_tc_wide.cu (streamed
+// weights, stashed activations), 128 < F_PAD <= 256 on the layer-wise kernels of brief_tc_lw.cu.
 #include "brief_tc_common.cuh"
 
 namespace brief {
