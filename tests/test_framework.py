@@ -220,3 +220,34 @@ def test_warm_start_from_a_compressed_directory(tmp_path):
     for c, f, w in zip(cold, first, warm):
         assert w.loss < f.loss - 1.0                 # clearly below a cold first step ...
         assert abs(w.loss - c.loss) < 0.01 * c.loss  # ... and where the first run stopped (one Adamax step apart)
+
+
+def test_sampler_rules_follow_the_reference():
+    from brief_pytorch_b200.CompressFramework import NFGR
+    o = opt()
+    cf = NFGR(o, 0, "f16")
+    assert cf._sampler_name(64 ** 3, (64, 64, 64)) == "randomcube"
+    assert cf._sampler_name(96 ** 3, (96, 96, 96)) == "randompoint"       # main.py:332-334
+    o["Compress"]["sampler"]["cube_len"] = [8, 8, 8]                      # min(block, cube) = 512 <= 80^3: stays a cube sampler,
+    with pytest.raises(NotImplementedError):                             # but sliding 8^3 cubes are not the fused form
+        NFGR(o, 0, "f16")._sampler_name(96 ** 3, (96, 96, 96))
+    o["Compress"]["sampler"].update(cube_len=[10000000] * 3, cube_count=2)
+    with pytest.raises(NotImplementedError):
+        NFGR(o, 0, "f16")._sampler_name(64 ** 3, (64, 64, 64))
+
+
+def test_exception_merge_and_volume_reader(tmp_path):
+    """OmegaConf.merge semantics for Compress.divide.exception (main.py:568-569) and the .npy reader of NFGR.compress."""
+    from brief_pytorch_b200.CompressFramework import _merge, read_volume
+    base = {"Compress": {"lr_phi": 1e-3, "sampler": {"name": "randomcube", "sample_size": 5}}, "Module": {"phi": {"layers": 7}}}
+    over = {"Compress": {"sampler": {"sample_size": 9}}, "Module": {"phi": {"layers": 5, "w0": 20}}}
+    got = _merge(base, over)
+    assert got == {"Compress": {"lr_phi": 1e-3, "sampler": {"name": "randomcube", "sample_size": 9}},
+                   "Module": {"phi": {"layers": 5, "w0": 20}}}
+    assert base["Module"]["phi"] == {"layers": 7}  # inputs untouched
+    vol = (np.arange(2 * 3 * 4) * 7).astype(np.uint16).reshape(2, 3, 4)
+    np.save(tmp_path / "v.npy", vol)
+    r = read_volume(str(tmp_path / "v.npy"))
+    assert r.shape == (2, 3, 4, 1) and r.dtype == np.uint16 and (r[..., 0] == vol).all()
+    np.save(tmp_path / "w.npy", vol[..., None])
+    assert read_volume(str(tmp_path / "w.npy")).shape == (2, 3, 4, 1)

@@ -209,20 +209,6 @@ def test_divide_exception_overrides_one_blocks_configuration():
         assert np.abs(pack_module_params(b.module) - p0).max() > 1e-4
 
 
-def test_sampler_rules_follow_the_reference():
-    from brief_pytorch_b200.CompressFramework import NFGR
-    o = opt()
-    cf = NFGR(o, 0, "f16")
-    assert cf._sampler_name(64 ** 3, (64, 64, 64)) == "randomcube"
-    assert cf._sampler_name(96 ** 3, (96, 96, 96)) == "randompoint"       # main.py:332-334
-    o["Compress"]["sampler"]["cube_len"] = [8, 8, 8]                      # min(block, cube) = 512 <= 80^3: stays a cube sampler,
-    with pytest.raises(NotImplementedError):                             # but sliding 8^3 cubes are not the fused form
-        NFGR(o, 0, "f16")._sampler_name(96 ** 3, (96, 96, 96))
-    o["Compress"]["sampler"].update(cube_len=[10000000] * 3, cube_count=2)
-    with pytest.raises(NotImplementedError):
-        NFGR(o, 0, "f16")._sampler_name(64 ** 3, (64, 64, 64))
-
-
 def test_single_task_compress_entry_writes_the_reference_layout(tmp_path):
     """NFGR.compress(data_path) (main.py:322-454): checkpoints -> steps{N}/compressed/{sideinfos.yaml, module/*}, decoded
     quality rows in performance.csv; the oracle decodes the written module to the volume our decode gives."""
