@@ -153,8 +153,7 @@ class NFGR:
 
     # ---- fit (main.py:322-454 for every block at once) -----------------------------------------------------------
     def _sampler_name(self, n_vox: int, shape) -> str:
-        """main.py:325-334: the cube sampler survives only while min(block voxels, clamped cube voxels) <= 80^3; of the
-        cube sampler only the shipped whole-block form (cube_count 1, cube_len >= block) is fused."""
+        """main.py:325-334: the cube sampler survives only while min(block voxels, configured cube voxels) <= 80^3."""
         sp = self.opt["Compress"]["sampler"]
         name = sp["name"]
         if name not in ("randomcube", "randompoint"):
@@ -164,11 +163,21 @@ class NFGR:
             cube = cube_len[0] * cube_len[1] * cube_len[2] if len(shape) == 3 else cube_len[1] * cube_len[2]
             if min(n_vox, cube) > 80 ** 3:
                 return "randompoint"
-            dims = list(shape)[-3:] if len(shape) >= 3 else [1] + list(shape)
-            if int(sp.get("cube_count", 1)) != 1 or any(c < n for c, n in zip(cube_len[-len(dims):], dims)):
-                raise NotImplementedError("only whole-block cubes (cube_count 1, cube_len >= block: every shipped config) are "
-                                          "fused; general sliding cubes are not part of this path")
         return name
+
+    def _cube_config(self, shape):
+        """(cube_count, cube_len clamped to the block) of the cube sampler (main.py:49-50, 367-369)."""
+        sp = self.opt["Compress"]["sampler"]
+        cube_len = [int(c) for c in sp.get("cube_len", [10000000] * 3)]
+        return int(sp.get("cube_count", 1)), [min(c, int(n)) for c, n in zip(cube_len, shape)]
+
+    def _step_batch(self, shape) -> int:
+        """Samples one step draws from a block of this shape."""
+        n_vox = int(np.prod(shape))
+        if self._sampler_name(n_vox, shape) == "randompoint":
+            return int(self.opt["Compress"]["sampler"]["sample_size"])
+        count, clen = self._cube_config(shape)
+        return count * int(np.prod(clen))
 
     def fit_blocks(self, blocks: Sequence[Block], max_steps: Optional[int] = None, seed: int = 42,
                    sampler_generator: str = "device", on_checkpoint=None,
@@ -255,12 +264,16 @@ class NFGR:
             if flat:
                 grp.set_denorm(i, vmin, vmax, lo, hi)
             self._keep.append((t, weight))
-            grp.set_sampler(i, self._sampler_name(int(np.prod(b.shape)), b.shape), int(C["sampler"]["sample_size"]))
+            if self._sampler_name(int(np.prod(b.shape)), b.shape) == "randomcube":
+                # windows of cube_len slid over the block; the shipped cube_len >= block, cube_count 1 is the whole block
+                grp.set_cube_sampler(i, *self._cube_config(b.shape))
+            else:
+                grp.set_sampler(i, "randompoint", int(C["sampler"]["sample_size"]))
         opt = misc.configure_lr_scheduler(misc.configure_optimizer(None, C["optimizer_name_phi"], C["lr_phi"]),
                                           C["lr_scheduler_phi"])
         done = 0
         for ck in checkpoints:
-            hist = grp.fit_run(ck - done, opt.name, opt.lr, opt.betas, opt.eps, opt.milestones, opt.gamma, seed=seed,
+            hist = grp.fit_run(ck - done, opt.name, opt.lr, opt.betas, opt.eps, opt.milestones_until(max_steps), opt.gamma, seed=seed,
                                loss_history=True)
             done = ck
             last = hist[-1].cpu().numpy() if hist is not None and len(hist) else np.full(len(blocks), np.nan)
@@ -413,8 +426,7 @@ class NFGR:
             if given:
                 b.param_size = float(given)
             b.features, _ = cf.estimate_module_size(b.param_size)
-            n_vox = int(np.prod(b.shape))
-            batch = n_vox if cf._sampler_name(n_vox, b.shape) == "randomcube" else int(cf.opt["Compress"]["sampler"]["sample_size"])
+            batch = cf._step_batch(b.shape)
             bsteps = steps if (not key or max_steps is not None) else int(cf.opt["Compress"]["max_steps"])
             costs.append(sharding.block_cost(b.features, cf.opt["Module"]["phi"]["layers"], batch, bsteps))
         owner = sharding.lpt_assign(costs, world)

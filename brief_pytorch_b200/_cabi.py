@@ -49,6 +49,7 @@ PROTOTYPES = {
     "brief_group_num_nets": (c_i32, [c_vp]),
     "brief_group_param_count": (c_i32, [c_vp, c_i32]),
     "brief_group_precision": (c_i32, [c_vp, c_i32]),
+    "brief_group_batch": (c_i32, [c_vp, c_i32]),
     "brief_group_set_params": (c_i32, [c_vp, c_i32, c_vp, c_vp]),
     "brief_group_get_params": (c_i32, [c_vp, c_i32, c_vp, c_vp]),
     "brief_group_get_grads": (c_i32, [c_vp, c_i32, c_vp, c_vp]),
@@ -59,6 +60,8 @@ PROTOTYPES = {
     "brief_group_bind_volume": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_f32, c_f32, c_f32, c_f32, c_vp,
                                         C.POINTER(WeightRule), c_i32, c_f32]),
     "brief_group_set_sampler": (c_i32, [c_vp, c_i32, c_i32, c_i32]),
+    "brief_group_set_cube_sampler": (c_i32, [c_vp, c_i32, c_i32, C.POINTER(c_i32)]),
+    "brief_cube_indices": (c_i32, [c_vp, c_i32, c_vp, c_u64, c_u64, c_vp, c_vp]),
     "brief_group_set_stream": (c_i32, [c_vp, c_i32, C.c_uint32]),
     "brief_group_set_slicing": (c_i32, [c_vp, c_i32]),
     "brief_fit_step": (c_i32, [c_vp, c_vp, c_u64, c_u64, c_vp, c_vp]),

@@ -163,6 +163,14 @@ struct BriefGroup {
   DevBuf<int> d_lw_fit_tab, d_lw_eval_tab;
   DevBuf<long long> d_lw_fit_base, d_lw_eval_base;
   DevBuf<unsigned char> d_lw_scratch;
+  // general sliding-cube samplers (brief_group_set_cube_sampler).  Host-side only: on the device such a network is a
+  // RANDOM_POINTS network of cube_count * cube voxels per step whose indices are read from the step's generated index
+  // buffer (gen_indices_kernel), so the fit kernels are the ones of the replayed-index mode
+  struct CubeCfg { int count = 0; int len[3] = {0, 0, 0}; };
+  std::vector<CubeCfg> cubes;
+  bool any_cube = false;
+  long long idx_total = 0;         // entries of a step's index array (all RANDOM_POINTS networks, finalize)
+  DevBuf<long long> d_gen_idx;
 };
 
 namespace {
@@ -515,6 +523,10 @@ int finalize(BriefGroup* g, cudaStream_t st) {
   if (stash_total > 0) CU(g->d_stash.ensure(stash_total));
   CU(g->d_loss_partials.ensure((size_t)slice_total));
   CU(g->d_loss_scratch.ensure((size_t)g->n_nets));
+  g->idx_total = idx_total;
+  g->any_cube = false;
+  for (const auto& c : g->cubes) g->any_cube |= c.count > 0;
+  if (g->any_cube) CU(g->d_gen_idx.ensure((size_t)idx_total));
   g->nets_dirty = true;
   RC(sync_nets(g, st));
   g->work_dirty = false;
@@ -531,8 +543,34 @@ int ensure_wpack(BriefGroup* g, cudaStream_t st) {
 
 int launch_lw_fit(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st, const StepState* state);
 
+// A step's explicit index array (layout: NetDev::idx_off) for a group that holds sliding-cube samplers: cube networks
+// expand their cubes, point networks get the stream they would have drawn on chip.  host_dev_cube_ids (optional, one
+// device pointer or NULL per network): replayed cube draws instead of the network's Philox stream.
+int generate_step_indices(BriefGroup* g, const int64_t* const* host_dev_cube_ids, uint64_t seed, uint64_t step, cudaStream_t st,
+                          const StepState* state) {
+  for (int i = 0; i < g->n_nets; ++i) {
+    const NetDev& n = g->nets[i];
+    if (n.mode != BRIEF_SAMPLE_RANDOM_POINTS) continue;
+    const BriefGroup::CubeCfg& c = g->cubes[i];
+    long long* out = g->d_gen_idx.p + n.idx_off;
+    if (c.count == 0) {
+      LAUNCH(launch_gen_indices(seed, step, state, n.stream_id, n.batch, n.n_vox, n.h, n.w, 1, 1, 0, nullptr, out, st));
+    } else {
+      const long long pop = (long long)(n.d - c.len[0] + 1) * (n.h - c.len[1] + 1) * (n.w - c.len[2] + 1);
+      const long long cube_vox = (long long)c.len[0] * c.len[1] * c.len[2];
+      const long long* ids = host_dev_cube_ids ? reinterpret_cast<const long long*>(host_dev_cube_ids[i]) : nullptr;
+      LAUNCH(launch_gen_indices(seed, step, state, n.stream_id, n.batch, pop, n.h, n.w, c.len[1], c.len[2], cube_vox, ids, out, st));
+    }
+  }
+  return 0;
+}
+
 int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st,
                        const StepState* state = nullptr) {
+  if (!dev_idx && g->any_cube) {
+    RC(generate_step_indices(g, nullptr, seed, step, st, state));
+    dev_idx = reinterpret_cast<const int64_t*>(g->d_gen_idx.p);
+  }
   FitArgs a{};
   a.nets = g->d_nets.p;
   a.params = g->d_params.p;
@@ -769,6 +807,7 @@ int brief_group_create(const BriefNetDesc* descs, int32_t n_nets, int32_t device
   if (g->num_sms < 1) g->num_sms = 148;
   g->n_nets = n_nets;
   g->nets.resize(n_nets);
+  g->cubes.assign(n_nets, BriefGroup::CubeCfg{});
   auto bail = [&](int rc) { brief_group_destroy(g); return rc; };
   for (int i = 0; i < n_nets; ++i) {
     const BriefNetDesc& d = descs[i];
@@ -863,7 +902,7 @@ void brief_group_destroy(BriefGroup* g) {
   g->d_nets.release(); g->d_params.release(); g->d_grads.release(); g->d_m.release(); g->d_v.release();
   g->d_axes.release(); g->d_partials.release(); g->d_loss_partials.release(); g->d_loss_scratch.release();
   g->d_lw_fit_tab.release(); g->d_lw_eval_tab.release(); g->d_lw_fit_base.release(); g->d_lw_eval_base.release();
-  g->d_lw_scratch.release();
+  g->d_lw_scratch.release(); g->d_gen_idx.release();
   g->d_wpack.release(); g->d_stash.release(); g->d_fit_tables.release(); g->d_eval_tables.release(); g->d_outptrs.release();
   delete g;
 }
@@ -876,6 +915,10 @@ int brief_group_param_count(const BriefGroup* g, int32_t net) {
 int brief_group_precision(const BriefGroup* g, int32_t net) {
   RC(check_net(g, net));
   return g->nets[net].prec;
+}
+int brief_group_batch(const BriefGroup* g, int32_t net) {
+  RC(check_net(g, net));
+  return g->nets[net].batch;
 }
 
 static int arena_put(BriefGroup* g, int net, float* arena, const float* host_packed, cudaStream_t st) {
@@ -983,8 +1026,50 @@ int brief_group_set_sampler(BriefGroup* g, int32_t net, int32_t mode, int32_t ba
   NetDev& n = g->nets[net];
   n.mode = mode;
   n.batch = mode == BRIEF_SAMPLE_FULL_BLOCK ? (int)std::min<long long>(n.n_vox, 0x7fffffffLL) : batch;
+  g->cubes[net] = BriefGroup::CubeCfg{};
   g->work_dirty = true;
   g->nets_dirty = true;
+  return 0;
+}
+
+int brief_group_set_cube_sampler(BriefGroup* g, int32_t net, int32_t cube_count, const int32_t* host_cube_len) {
+  RC(check_net(g, net));
+  if (!host_cube_len || cube_count < 1) return fail(BRIEF_ERR_INVALID, "cube_count=%d", cube_count);
+  NetDev& n = g->nets[net];
+  const int dims[3] = {n.d, n.h, n.w};
+  BriefGroup::CubeCfg c;
+  long long vox = 1, pop = 1;
+  for (int k = 0; k < 3; ++k) {
+    if (host_cube_len[k] < 1) return fail(BRIEF_ERR_INVALID, "cube_len[%d]=%d", k, host_cube_len[k]);
+    c.len[k] = std::min(host_cube_len[k], dims[k]);  // main.py:49-50
+    vox *= c.len[k];
+    pop *= dims[k] - c.len[k] + 1;
+  }
+  if (pop == 1 && cube_count == 1) return brief_group_set_sampler(g, net, BRIEF_SAMPLE_FULL_BLOCK, 0);
+  if (vox * cube_count > 0x7fffffffLL)
+    return fail(BRIEF_ERR_UNSUPPORTED, "%d cubes of %lld voxels exceed the per-step sample limit", cube_count, vox);
+  if (pop > 0xffffffffLL) return fail(BRIEF_ERR_UNSUPPORTED, "cube population %lld exceeds the sampler stream's range", pop);
+  c.count = cube_count;
+  g->cubes[net] = c;
+  n.mode = BRIEF_SAMPLE_RANDOM_POINTS;
+  n.batch = (int)(vox * cube_count);
+  g->work_dirty = true;
+  g->nets_dirty = true;
+  return 0;
+}
+
+int brief_cube_indices(BriefGroup* g, int32_t net, const int64_t* dev_cube_ids, uint64_t seed, uint64_t step, int64_t* dev_out,
+                       void* stream) {
+  RC(check_net(g, net));
+  if (!dev_out) return fail(BRIEF_ERR_INVALID, "null output");
+  const BriefGroup::CubeCfg& c = g->cubes[net];
+  if (c.count == 0) return fail(BRIEF_ERR_STATE, "net %d has no sliding-cube sampler (brief_group_set_cube_sampler)", net);
+  RC(use_device(g));
+  const NetDev& n = g->nets[net];
+  const long long pop = (long long)(n.d - c.len[0] + 1) * (n.h - c.len[1] + 1) * (n.w - c.len[2] + 1);
+  LAUNCH(launch_gen_indices(seed, step, nullptr, n.stream_id, n.batch, pop, n.h, n.w, c.len[1], c.len[2],
+                            (long long)c.len[0] * c.len[1] * c.len[2], reinterpret_cast<const long long*>(dev_cube_ids),
+                            reinterpret_cast<long long*>(dev_out), (cudaStream_t)stream));
   return 0;
 }
 

@@ -101,6 +101,15 @@ __host__ __device__ inline long long brief_sample_index(uint64_t seed, uint64_t 
   return (long long)(((uint64_t)word * pop) >> 32);
 }
 
+// General RandomCubeSampler (main.py:61-69, 112-116): the population is every position of a ch x cw (x cd) window slid
+// over the block with stride 1, listed '(dc hc wc)'; sample o of cube `cube` in 'ds hs ws' order is this voxel.
+__host__ __device__ inline long long brief_cube_voxel(int h, int w, int ch, int cw, long long cube, long long o) {
+  const long long HC = h - ch + 1, WC = w - cw + 1;
+  const long long wc = cube % WC, r = cube / WC, hc = r % HC, dc = r / HC;
+  const long long ws = o % cw, q = o / cw, hs = q % ch, ds = q / ch;
+  return ((dc + ds) * h + (hc + hs)) * w + (wc + ws);
+}
+
 #ifdef __CUDACC__
 // ---- per-sample input fetch ------------------------------------------------------------------
 __device__ __forceinline__ float brief_raw_value(const NetDev& n, long long idx) {

@@ -128,6 +128,9 @@ cudaError_t launch_gather(const NetDev* nets, int net_id, const float* axes, con
                           float* coords, float* data, float* weight, cudaStream_t st);
 cudaError_t launch_sample_indices(uint64_t seed, uint64_t step, uint32_t net, long long batch, long long pop,
                                   long long* out, cudaStream_t st);
+cudaError_t launch_gen_indices(uint64_t seed, uint64_t step, const StepState* state, uint32_t stream, long long batch,
+                               long long pop, int h, int w, int ch, int cw, long long cube_vox, const long long* cube_ids,
+                               long long* out, cudaStream_t st);
 
 // brief_data.cu
 cudaError_t launch_block_stats(const void* const* dev_ptrs, const long long* dev_sizes, int n_blocks, long long max_size,

@@ -416,6 +416,25 @@ __global__ void sample_indices_kernel(uint64_t seed, uint64_t step, uint32_t net
     out[i] = brief_sample_index(seed, step, net, (uint64_t)i, (uint64_t)pop);
 }
 
+// One network's slice of the step's explicit index buffer, written when a group holds sliding-cube samplers (the fit
+// kernels then run in their replayed-index mode).  cube_vox == 0: `batch` point indices, the stream the fit kernels draw
+// on chip.  cube_vox > 0: batch / cube_vox cubes of cube_vox voxels each; cube c is cube_ids[c] when the caller replays
+// the reference's torch.randint draws (main.py:114), else draw c of the network's Philox stream over the `pop` cubes.
+__global__ void gen_indices_kernel(uint64_t seed, uint64_t step, const StepState* state, uint32_t stream, long long batch,
+                                   long long pop, int h, int w, int ch, int cw, long long cube_vox,
+                                   const long long* __restrict__ cube_ids, long long* out) {
+  if (state) step = state->step;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < batch; i += (long long)gridDim.x * blockDim.x) {
+    if (cube_vox == 0) {
+      out[i] = brief_sample_index(seed, step, stream, (uint64_t)i, (uint64_t)pop);
+    } else {
+      const long long c = i / cube_vox, o = i - c * cube_vox;
+      const long long cube = cube_ids ? __ldg(cube_ids + c) : brief_sample_index(seed, step, stream, (uint64_t)c, (uint64_t)pop);
+      out[i] = brief_cube_voxel(h, w, ch, cw, cube, o);
+    }
+  }
+}
+
 // ---- host launchers ------------------------------------------------------------------------------------
 // A tile of TM <= 32 rows (wide networks: the activations of all layers fill shared memory, one CTA per SM) is served
 // by 512 threads — 16 output-feature groups per row instead of 4 — so that the SM has 16 warps to hide latency with.
@@ -463,6 +482,17 @@ cudaError_t launch_sample_indices(uint64_t seed, uint64_t step, uint32_t net, lo
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   sample_indices_kernel<<<(int)blocks, threads, 0, st>>>(seed, step, net, batch, pop, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gen_indices(uint64_t seed, uint64_t step, const StepState* state, uint32_t stream, long long batch,
+                               long long pop, int h, int w, int ch, int cw, long long cube_vox, const long long* cube_ids,
+                               long long* out, cudaStream_t st) {
+  const int threads = 256;
+  long long blocks = (batch + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  gen_indices_kernel<<<(int)blocks, threads, 0, st>>>(seed, step, state, stream, batch, pop, h, w, ch, cw, cube_vox, cube_ids, out);
   return cudaGetLastError();
 }
 

@@ -39,6 +39,22 @@ class NetSpec:
         return c * f + f + (L - 2) * (f * f + f) + f * o + o
 
 
+def schedule_window(lr: float, milestones: Sequence[int], gamma: float, steps_done: int):
+    """BriefOptConfig carries at most 8 MultiStepLR milestones.  Returns (lr0, window, horizon): the configuration that
+    reproduces the schedule `milestones` from step steps_done + 1 until `horizon` steps are complete (None: for ever).
+    Up to 8 milestones pass through unchanged; longer lists (a StepLR expressed as milestones, utils/misc.py:191-192)
+    are served window by window, with the decays already behind folded into lr0 by the same chained multiplication."""
+    ms = sorted(int(m) for m in milestones)
+    if len(ms) <= 8:
+        return float(lr), ms, None
+    lr0 = float(np.float32(lr))
+    for m in ms:
+        if m <= steps_done:
+            lr0 *= float(np.float32(gamma))
+    pending = [m for m in ms if m > steps_done]
+    return lr0, pending[:8], (pending[8] if len(pending) > 8 else None)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -88,6 +104,7 @@ class SirenGroup:
             torch.cuda.current_stream()  # make sure the primary context exists
             check(self._lib.brief_group_create(descs, len(self.specs), idx, _PREC[precision], C.byref(self._h)))
         self._keep: Dict[int, tuple] = {}  # tensors bound to the group must outlive it
+        self._cube_count: Dict[int, int] = {}
         self.steps_done = 0
 
     # ---- life cycle -------------------------------------------------------------------------------
@@ -191,6 +208,31 @@ class SirenGroup:
     def set_sampler(self, net: int, mode: str, batch: int = 0) -> None:
         m = {"randomcube": SAMPLE_FULL_BLOCK, "full": SAMPLE_FULL_BLOCK, "randompoint": SAMPLE_RANDOM_POINTS}[mode]
         check(self._lib.brief_group_set_sampler(self._h, net, m, int(batch)))
+        self._cube_count.pop(net, None)
+
+    def set_cube_sampler(self, net: int, cube_count: int, cube_len: Sequence[int]) -> None:
+        """The general RandomCubeSampler (main.py:38-125): `cube_count` windows of `cube_len` voxels (clamped to the
+        block) per step.  cube_len covers the block's axes: (d,h,w), or (h,w) for a 2-D network."""
+        clen = [int(c) for c in cube_len]
+        if len(clen) == 2:
+            clen = [1] + clen
+        check(self._lib.brief_group_set_cube_sampler(self._h, net, int(cube_count), (C.c_int32 * 3)(*clen)))
+        self._cube_count[net] = int(cube_count)
+
+    def cube_indices(self, net: int, cube_ids: Optional[torch.Tensor] = None, seed: int = 0, step: int = 0) -> torch.Tensor:
+        """Voxel indices (int64, cube after cube) of one step of a cube network: `cube_ids` = the step's window draws
+        (torch.randint(0, pop_size, (cube_count,)), main.py:114) or None for the on-device stream at (seed, step)."""
+        if cube_ids is not None:
+            assert cube_ids.numel() == self._cube_count.get(net), "one window index per cube of the step"
+            cube_ids = cube_ids.to(self.device, torch.int64).contiguous()
+        out = torch.empty(self.batch(net), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.brief_cube_indices(self._h, net, _ptr(cube_ids), seed, step, _ptr(out), _stream(self.device)))
+        return out
+
+    def batch(self, net: int) -> int:
+        """Samples per step of the network under its current sampler."""
+        return check(self._lib.brief_group_batch(self._h, net))
 
     def set_stream(self, net: int, stream_id: int) -> None:
         """Key of the network's on-device sampler stream (pass the block's global index when blocks are sharded)."""
@@ -227,14 +269,20 @@ class SirenGroup:
                 milestones: Sequence[int] = (), gamma: float = 0.2, seed: int = 42,
                 loss_history: bool = False) -> Optional[torch.Tensor]:
         """n_steps iterations of main.py:385-400 enqueued from C without host synchronisation."""
-        cfg = _cabi.OptConfig(_OPT[kind], lr, betas[0], betas[1], eps, len(milestones),
-                              (C.c_int64 * 8)(*list(milestones)[:8]), gamma)
         hist = torch.empty((n_steps, len(self.specs)), dtype=torch.float32, device=self.device) if loss_history else None
-        with torch.cuda.device(self.device):
-            check(self._lib.brief_fit_run(self._h, C.byref(cfg), seed, self.steps_done, n_steps, _ptr(hist),
-                                          _stream(self.device)))
-        self.steps_done += n_steps
-        return hist
+        done = 0
+        while True:
+            lr0, window, horizon = schedule_window(lr, milestones, gamma, self.steps_done)
+            n = n_steps - done if horizon is None else min(n_steps - done, horizon - self.steps_done)
+            cfg = _cabi.OptConfig(_OPT[kind], lr0, betas[0], betas[1], eps, len(window), (C.c_int64 * 8)(*window), gamma)
+            with torch.cuda.device(self.device):
+                check(self._lib.brief_fit_run(self._h, C.byref(cfg), seed, self.steps_done, n,
+                                              _ptr(hist[done:]) if hist is not None and done < n_steps else None,
+                                              _stream(self.device)))
+            self.steps_done += n
+            done += n
+            if done >= n_steps:
+                return hist
 
     def fit_step_host(self, host_idx: Optional[torch.Tensor], host_loss: Optional[torch.Tensor], kind: str = "Adamax",
                       lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, milestones: Sequence[int] = (),
@@ -250,8 +298,8 @@ class SirenGroup:
             assert host_idx.dtype == torch.int64
         if host_loss is not None:
             assert host_loss.dtype == torch.float32 and host_loss.numel() >= len(self.specs)
-        cfg = _cabi.OptConfig(_OPT[kind], lr, betas[0], betas[1], eps, len(milestones),
-                              (C.c_int64 * 8)(*list(milestones)[:8]), gamma)
+        lr0, window, _ = schedule_window(lr, milestones, gamma, self.steps_done)
+        cfg = _cabi.OptConfig(_OPT[kind], lr0, betas[0], betas[1], eps, len(window), (C.c_int64 * 8)(*window), gamma)
         with torch.cuda.device(self.device):
             check(self._lib.brief_fit_step_host(self._h, _ptr(host_idx), C.byref(cfg), seed, self.steps_done,
                                                 _ptr(host_loss), _stream(self.device)))

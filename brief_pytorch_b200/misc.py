@@ -159,10 +159,17 @@ class FusedOptimizer:
     eps: float = 1e-8
     milestones: tuple = ()
     gamma: float = 1.0
+    step_size: int = 0   # StepLR: a decay every step_size steps (milestones are then generated per horizon)
+
+    def milestones_until(self, n_steps: int) -> tuple:
+        """The schedule as MultiStepLR milestones for a run of n_steps steps (what SirenGroup.fit_run consumes)."""
+        if self.step_size > 0:
+            return tuple(range(self.step_size, int(n_steps), self.step_size))
+        return self.milestones
 
     def lr_at(self, step_1based: int) -> float:
         lr = self.lr
-        for m in self.milestones:
+        for m in self.milestones_until(step_1based):
             if m <= step_1based - 1:
                 lr *= self.gamma
         return lr
@@ -180,9 +187,15 @@ def configure_lr_scheduler(optimizer: FusedOptimizer, lr_scheduler_opt) -> Fused
     if name == "MultiStepLR":
         optimizer.milestones = tuple(sorted(int(m) for m in opt["milestones"]))
         optimizer.gamma = float(opt.get("gamma", 0.1))
+        optimizer.step_size = 0
+    elif name == "StepLR":  # lr * gamma every step_size steps: MultiStepLR at the multiples of step_size
+        optimizer.milestones, optimizer.step_size = (), int(opt["step_size"])
+        optimizer.gamma = float(opt.get("gamma", 0.1))
+        if optimizer.step_size < 1:
+            raise ValueError("StepLR.step_size must be positive")
     elif name == "none":
-        optimizer.milestones, optimizer.gamma = (), 1.0
-    else:
+        optimizer.milestones, optimizer.gamma, optimizer.step_size = (), 1.0, 0
+    else:  # CyclicLR (utils/misc.py:189-190) changes lr AND beta1 every step; no shipped config uses it
         raise NotImplementedError(f"lr scheduler '{name}' is not used by any shipped config")
     return optimizer
 

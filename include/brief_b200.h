@@ -109,6 +109,7 @@ void brief_group_destroy(BriefGroup* g);
 int brief_group_num_nets(const BriefGroup* g);
 int brief_group_param_count(const BriefGroup* g, int32_t net);      /* SIREN.calc_param_count :291-297 */
 int brief_group_precision(const BriefGroup* g, int32_t net);        /* resolved BriefPrecision          */
+int brief_group_batch(const BriefGroup* g, int32_t net);            /* samples per step under the current sampler */
 
 /* Replaces load_model / save_model's tensor traffic (utils/ModelSave.py:8-51). Packed fp32, host. */
 int brief_group_set_params(BriefGroup* g, int32_t net, const float* host_packed, void* stream);
@@ -139,6 +140,21 @@ int brief_group_bind_volume(BriefGroup* g, int32_t net, const void* dev_raw, int
                             const BriefWeightRule* rules, int32_t n_rules, float tau);
 /* Sampler of main.py:367-371 for this network. `batch` is ignored for FULL_BLOCK (= voxel count). */
 int brief_group_set_sampler(BriefGroup* g, int32_t net, int32_t mode, int32_t batch);
+
+/* The GENERAL RandomCubeSampler (main.py:38-125, == utils/sampler.py:9-57): every step draws `cube_count` windows of
+ * cube_len voxels (clamped to the block, main.py:49-50; for 2-D data pass {1, len_h, len_w}) with replacement from all
+ * stride-1 window positions, listed '(dc hc wc)' (main.py:61-69), and the loss is the mean over all their voxels.
+ * A cube network then counts as a RANDOM_POINTS network of cube_count * prod(cube_len) samples per step: replayed
+ * indices (brief_fit_step's dev_idx, brief_fit_step_host's host_idx) are VOXEL indices in cube order — brief_cube_indices
+ * expands the reference's torch.randint cube draws (main.py:114) into them — and with the on-device sampler the cube
+ * draws come from the network's Philox stream (draw c of the step = cube c).  cube_len >= block with cube_count 1 (every
+ * shipped config) degenerates to BRIEF_SAMPLE_FULL_BLOCK.  brief_group_set_sampler on the network removes the cubes. */
+int brief_group_set_cube_sampler(BriefGroup* g, int32_t net, int32_t cube_count, const int32_t* host_cube_len);
+/* Voxel indices (int64, cube_count * prod(cube_len), cube after cube in 'ds hs ws' order) of one step of a cube
+ * network: dev_cube_ids = cube_count window indices (int64, device memory), or NULL for the on-device stream at
+ * (seed, step).  Asynchronous on `stream`. */
+int brief_cube_indices(BriefGroup* g, int32_t net, const int64_t* dev_cube_ids, uint64_t seed, uint64_t step,
+                       int64_t* dev_out, void* stream);
 
 /* Key of the network's on-device sampler stream (Philox counter word).  Default: the network's index in the group;
  * a caller that shards blocks over ranks passes the block's GLOBAL index so that a block draws the same samples

@@ -362,24 +362,28 @@ class RandompointSampler:
 
 
 class RandomCubeSampler:
-    """main.py:38-125, 3-D branch.  With the shipped cube_len (clamped to the block) and
-    cube_count=1 the population is one cube == the whole block every step."""
+    """main.py:38-125 (3-D branch :42-71, 2-D branch :73-102): cube_len is clamped to the block, the population is
+    every stride-1 window position listed '(dc hc wc)' / '(hc wc)', and a step is `cube_count` draws with replacement.
+    With the shipped cube_len (clamped to the block) and cube_count=1 the population is one cube == the whole block."""
 
     def __init__(self, data: torch.Tensor, weight: np.ndarray, coords_mode: str, cube_count: int,
                  cube_len: List[int], sample_count: int, device: str = "cpu", gpu_force: bool = False):
-        if data.dim() != 4:
+        nd = data.dim() - 1
+        if nd not in (2, 3):
             raise NotImplementedError
         self.sample_count = sample_count
-        d, h, w, c = data.shape
-        cube_len = [min(int(cube_len[i]), data.shape[i]) for i in range(3)]
-        coords = create_coords((d, h, w), mode=coords_mode)
+        cube_len = [min(int(cube_len[i]), data.shape[i]) for i in range(nd)]
+        self.cube_len = cube_len
+        coords = create_coords(tuple(data.shape[:nd]), mode=coords_mode)
         wt = torch.from_numpy(weight)
 
         def cubes(t):
-            u = t.unfold(0, cube_len[0], 1).unfold(1, cube_len[1], 1).unfold(2, cube_len[2], 1)
-            # [dc,hc,wc,c,ds,hs,ws] -> [(dc hc wc), ds, hs, ws, c]
-            u = u.permute(0, 1, 2, 4, 5, 6, 3)
-            return u.reshape(-1, cube_len[0], cube_len[1], cube_len[2], t.shape[-1])
+            u = t
+            for k in range(nd):
+                u = u.unfold(k, cube_len[k], 1)
+            # [dc,hc,wc,c,ds,hs,ws] -> [(dc hc wc), ds, hs, ws, c]   (2-D: [hc,wc,c,hs,ws] -> [(hc wc), hs, ws, c])
+            u = u.permute(*range(nd), *range(nd + 1, 2 * nd + 1), nd)
+            return u.reshape(-1, *cube_len, t.shape[-1])
 
         self.coords_cubes, self.data_cubes, self.weight_cubes = cubes(coords), cubes(data), cubes(wt)
         self.pop_size = self.data_cubes.shape[0]
@@ -400,6 +404,19 @@ class RandomCubeSampler:
         self.last_idx = idx
         self.index += 1
         return self.coords_cubes[idx], self.data_cubes[idx], self.weight_cubes[idx]
+
+
+def cube_voxel_indices(shape: Sequence[int], cube_len: Sequence[int], cube_ids) -> np.ndarray:
+    """Flat voxel indices [n_cubes, prod(cube_len)] of windows `cube_ids` of RandomCubeSampler's population
+    (main.py:61-69: unfold along every axis with stride 1, cubes listed row-major over their origins, voxels of a cube
+    row-major).  This is what brief_common.cuh's brief_cube_voxel restates on the device."""
+    shape = [int(n) for n in shape]
+    clen = [min(int(c), n) for c, n in zip(cube_len, shape)]
+    counts = [n - c + 1 for n, c in zip(shape, clen)]
+    origin = np.stack(np.unravel_index(np.asarray(cube_ids, dtype=np.int64), counts), axis=-1)      # [n, nd]
+    offs = np.stack(np.unravel_index(np.arange(int(np.prod(clen)), dtype=np.int64), clen), axis=-1)  # [v, nd]
+    pos = origin[:, None, :] + offs[None, :, :]
+    return np.ravel_multi_index(tuple(pos[..., k] for k in range(len(shape))), shape).astype(np.int64)
 
 
 # --------------------------------------------------------------------------------------

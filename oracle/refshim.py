@@ -96,3 +96,20 @@ def load_reference() -> types.SimpleNamespace:
     ns.tool = importlib.import_module("utils.tool")
     _REF = ns
     return ns
+
+
+def load_main_samplers() -> types.SimpleNamespace:
+    """The LIVE sampler classes of the reference, main.py:38-163.  main.py cannot be imported (argparse / OmegaConf
+    globals at module level), so the two class definitions are cut out of its syntax tree and executed unmodified in a
+    namespace that holds exactly the names they use (torch, np, rearrange, typing, utils.dataset.create_*coords)."""
+    import ast
+    load_reference()
+    with open(os.path.join(REFERENCE_ROOT, "main.py")) as fh:
+        tree = ast.parse(fh.read())
+    ns: dict = {}
+    exec("import torch\nimport numpy as np\nfrom einops import rearrange\nfrom typing import *\n"
+         "from utils.dataset import create_coords, create_flattened_coords\n", ns)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in ("RandomCubeSampler", "RandompointSampler"):
+            exec(compile(ast.Module([node], []), os.path.join(REFERENCE_ROOT, "main.py"), "exec"), ns)
+    return types.SimpleNamespace(RandomCubeSampler=ns["RandomCubeSampler"], RandompointSampler=ns["RandompointSampler"])

@@ -228,11 +228,10 @@ def test_sampler_rules_follow_the_reference():
     cf = NFGR(o, 0, "f16")
     assert cf._sampler_name(64 ** 3, (64, 64, 64)) == "randomcube"
     assert cf._sampler_name(96 ** 3, (96, 96, 96)) == "randompoint"       # main.py:332-334
-    o["Compress"]["sampler"]["cube_len"] = [8, 8, 8]                      # min(block, cube) = 512 <= 80^3: stays a cube sampler,
-    with pytest.raises(NotImplementedError):                             # but sliding 8^3 cubes are not the fused form
-        NFGR(o, 0, "f16")._sampler_name(96 ** 3, (96, 96, 96))
-    o["Compress"]["sampler"].update(cube_len=[10000000] * 3, cube_count=2)
-    with pytest.raises(NotImplementedError):
+    o["Compress"]["sampler"]["cube_len"] = [8, 8, 8]                      # min(block, cube) = 512 <= 80^3: stays a cube sampler
+    assert NFGR(o, 0, "f16")._sampler_name(96 ** 3, (96, 96, 96)) == "randomcube"   # (sliding cubes: tests/test_cubes.py)
+    o["Compress"]["sampler"]["name"] = "gridsampler"
+    with pytest.raises(NotImplementedError):                             # main.py:371
         NFGR(o, 0, "f16")._sampler_name(64 ** 3, (64, 64, 64))
 
 
