@@ -273,8 +273,13 @@ class NFGR:
                                           C["lr_scheduler_phi"])
         done = 0
         for ck in checkpoints:
-            hist = grp.fit_run(ck - done, opt.name, opt.lr, opt.betas, opt.eps, opt.milestones_until(max_steps), opt.gamma, seed=seed,
-                               loss_history=True)
+            if opt.cyclic is not None:  # CyclicLR: lr and beta1 of every step from torch's scheduler, one enqueue per step
+                hist = None
+                for lr_t, b1_t in opt.per_step(done + 1, ck - done):
+                    hist = grp.fit_run(1, opt.name, lr_t, (b1_t, opt.betas[1]), opt.eps, seed=seed, loss_history=True)
+            else:
+                hist = grp.fit_run(ck - done, opt.name, opt.lr, opt.betas, opt.eps, opt.milestones_until(max_steps), opt.gamma,
+                                   seed=seed, loss_history=True)
             done = ck
             last = hist[-1].cpu().numpy() if hist is not None and len(hist) else np.full(len(blocks), np.nan)
             for i, b in enumerate(blocks):

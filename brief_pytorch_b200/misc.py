@@ -5,7 +5,7 @@ from __future__ import annotations
 import copy
 import math
 from dataclasses import dataclass, field
-from typing import Callable, Iterable, List, Sequence
+from typing import Callable, Iterable, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -160,6 +160,27 @@ class FusedOptimizer:
     milestones: tuple = ()
     gamma: float = 1.0
     step_size: int = 0   # StepLR: a decay every step_size steps (milestones are then generated per horizon)
+    cyclic: Optional[dict] = None   # CyclicLR keyword arguments: lr AND beta1 change every step (per_step)
+    _cyc: Optional[tuple] = field(default=None, repr=False, compare=False)
+
+    def per_step(self, first_step_1based: int, n: int):
+        """CyclicLR (utils/misc.py:189-190): the (lr, beta1) of steps first .. first + n - 1, read off torch's OWN scheduler
+        driven on a dummy parameter — host scalars only, exactly the values the reference's optimiser would hold (with
+        cycle_momentum, torch cycles beta1 of Adam / Adamax between base_momentum and max_momentum)."""
+        if self._cyc is None or self._cyc[2] > first_step_1based - 1:
+            dummy = torch.nn.Parameter(torch.zeros(1))
+            topt = getattr(torch.optim, self.name)([dummy], lr=self.lr)
+            self._cyc = [topt, torch.optim.lr_scheduler.CyclicLR(topt, **self.cyclic), 0]
+        topt, sch, _ = self._cyc
+        out = []
+        for t in range(first_step_1based, first_step_1based + n):
+            while self._cyc[2] < t - 1:
+                topt.step()
+                sch.step()
+                self._cyc[2] += 1
+            grp = topt.param_groups[0]
+            out.append((float(grp["lr"]), float(grp["betas"][0]) if "betas" in grp else self.betas[0]))
+        return out
 
     def milestones_until(self, n_steps: int) -> tuple:
         """The schedule as MultiStepLR milestones for a run of n_steps steps (what SirenGroup.fit_run consumes)."""
@@ -168,6 +189,8 @@ class FusedOptimizer:
         return self.milestones
 
     def lr_at(self, step_1based: int) -> float:
+        if self.cyclic is not None:
+            return self.per_step(step_1based, 1)[0][0]
         lr = self.lr
         for m in self.milestones_until(step_1based):
             if m <= step_1based - 1:
@@ -187,16 +210,21 @@ def configure_lr_scheduler(optimizer: FusedOptimizer, lr_scheduler_opt) -> Fused
     if name == "MultiStepLR":
         optimizer.milestones = tuple(sorted(int(m) for m in opt["milestones"]))
         optimizer.gamma = float(opt.get("gamma", 0.1))
-        optimizer.step_size = 0
+        optimizer.step_size, optimizer.cyclic = 0, None
     elif name == "StepLR":  # lr * gamma every step_size steps: MultiStepLR at the multiples of step_size
-        optimizer.milestones, optimizer.step_size = (), int(opt["step_size"])
+        optimizer.milestones, optimizer.step_size, optimizer.cyclic = (), int(opt["step_size"]), None
         optimizer.gamma = float(opt.get("gamma", 0.1))
         if optimizer.step_size < 1:
             raise ValueError("StepLR.step_size must be positive")
     elif name == "none":
-        optimizer.milestones, optimizer.gamma, optimizer.step_size = (), 1.0, 0
-    else:  # CyclicLR (utils/misc.py:189-190) changes lr AND beta1 every step; no shipped config uses it
-        raise NotImplementedError(f"lr scheduler '{name}' is not used by any shipped config")
+        optimizer.milestones, optimizer.gamma, optimizer.step_size, optimizer.cyclic = (), 1.0, 0, None
+    elif name == "CyclicLR":  # lr (and beta1) of every step come from torch's scheduler itself, see per_step
+        if optimizer.name == "SGD" and opt.get("cycle_momentum", True):
+            raise NotImplementedError("CyclicLR with cycle_momentum turns torch's SGD into momentum SGD; the fused SGD has none")
+        optimizer.milestones, optimizer.gamma, optimizer.step_size, optimizer.cyclic = (), 1.0, 0, opt
+        optimizer._cyc = None
+    else:
+        raise NotImplementedError(name)  # utils/misc.py:195-196
     return optimizer
 
 

@@ -443,13 +443,15 @@ def configure_optimizer(parameters, optimizer: str, lr: float):
 
 
 def configure_lr_scheduler(optimizer, lr_scheduler_opt: dict):
-    """utils/misc.py:184-197 (MultiStepLR / none / StepLR)."""
+    """utils/misc.py:184-197 (MultiStepLR / CyclicLR / StepLR / none)."""
     opt = copy.deepcopy(dict(lr_scheduler_opt))
     name = opt.pop("name")
     if name == "MultiStepLR":
         return torch.optim.lr_scheduler.MultiStepLR(optimizer, **opt)
     if name == "StepLR":
         return torch.optim.lr_scheduler.StepLR(optimizer, **opt)
+    if name == "CyclicLR":
+        return torch.optim.lr_scheduler.CyclicLR(optimizer, **opt)
     if name == "none":
         return torch.optim.lr_scheduler.MultiStepLR(optimizer, milestones=[100000000000])
     raise NotImplementedError

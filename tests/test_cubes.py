@@ -128,7 +128,31 @@ def test_schedules_with_more_than_eight_decays():
     for t in range(1, 41):
         assert abs(opt.lr_at(t) - g["c3d_lrs"][t - 1]) < 1e-15
     with pytest.raises(NotImplementedError):
-        misc.configure_lr_scheduler(opt, {"name": "CyclicLR", "base_lr": 1e-4, "max_lr": 1e-3})
+        misc.configure_lr_scheduler(opt, {"name": "CosineAnnealingLR", "T_max": 10})   # utils/misc.py:195-196
+
+
+@pytest.mark.parametrize("name", ["Adamax", "Adam"])
+def test_cyclic_lr_schedule_is_torchs_own(name):
+    """CyclicLR (utils/misc.py:189-190) changes lr and, with cycle_momentum, beta1 every step: FusedOptimizer.per_step
+    reads both off torch's scheduler, so they equal what the reference's optimiser holds at every step, in any order."""
+    from brief_pytorch_b200 import misc
+    kw = {"name": "CyclicLR", "base_lr": 1e-4, "max_lr": 1e-3, "step_size_up": 4}
+    o = misc.configure_lr_scheduler(misc.configure_optimizer(None, name, 1e-3), kw)
+    got = o.per_step(1, 6) + o.per_step(7, 6)
+    p = torch.nn.Parameter(torch.zeros(1))
+    t = O.configure_optimizer([p], name, 1e-3)
+    sch = O.configure_lr_scheduler(t, kw)
+    want = []
+    for _ in range(12):
+        want.append((t.param_groups[0]["lr"], t.param_groups[0]["betas"][0]))
+        t.step()
+        sch.step()
+    assert got == want and want[0] == (1e-4, 0.9) and want[4] == (1e-3, 0.8)
+    assert o.per_step(3, 2) == want[2:4] and o.lr_at(5) == 1e-3            # rewinds
+    with pytest.raises(NotImplementedError):                               # torch would switch SGD to momentum SGD
+        misc.configure_lr_scheduler(misc.configure_optimizer(None, "SGD", 1e-3), kw)
+    sgd = misc.configure_lr_scheduler(misc.configure_optimizer(None, "SGD", 1e-3), dict(kw, cycle_momentum=False))
+    assert [lr for lr, _ in sgd.per_step(1, 5)] == [w[0] for w in want[:5]]
 
 
 def test_nfgr_sampler_choice_follows_main_py():

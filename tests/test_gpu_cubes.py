@@ -169,3 +169,32 @@ def test_divided_volume_with_sliding_cubes(tmp_path):
         assert np.isfinite(b.loss) and b.loss < b0.loss
     out = cf.decompress_divide(os.path.join(cdir, "sideinfos.yaml"), os.path.join(cdir, "module"), os.path.join(cdir, "sideinfos"))
     assert out.shape == vol.shape and out.dtype == vol.dtype
+
+
+def test_cyclic_lr_through_nfgr_matches_the_oracle():
+    """Compress.lr_scheduler_phi = CyclicLR (utils/misc.py:189-190): NFGR.fit_blocks walks torch's own schedule step by
+    step (lr and beta1); 20 whole-block Adamax steps against the oracle's loop with the same scheduler, fp32 mode."""
+    from brief_pytorch_b200 import synth
+    from brief_pytorch_b200.CompressFramework import NFGR, Block
+    sched, steps = {"name": "CyclicLR", "base_lr": 1e-4, "max_lr": 1e-2, "step_size_up": 3}, 20
+    vol = synth.vessel((16, 24, 24), seed=7)
+    final = {}
+    for name, sc in (("cyclic", sched), ("none", {"name": "none"})):
+        o = vessel_opt()
+        o["Compress"]["checkpoints"] = "none"
+        o["Compress"]["lr_scheduler_phi"] = sc
+        blk = Block("d_0_15-h_0_23-w_0_23", vol, [0, 15], [0, 23], [0, 23], 4.0 * 1700)
+        NFGR(o, 0, "fp32").fit_blocks([blk], max_steps=steps).close()
+        final[name] = blk.loss
+    weight = O.parse_weight(vol.copy(), ["value_65535_65535_1"])
+    data_t, side = O.normalize_data(vol.copy(), "minmaxany_0_100")
+    thr = O.weight_thres_normalized(65535, "minmaxany_0_100", side["min"], side["max"])
+    torch.manual_seed(42)
+    phi = O.init_phi(dict(coords_channel=3, data_channel=1, layers=7, name="SIREN", w0=10, features=blk.features))
+    topt = O.configure_optimizer(phi.parameters(), "Adamax", 1e-3)
+    sch = O.configure_lr_scheduler(topt, sched)
+    sampler = O.RandomCubeSampler(data_t, weight, "-1,1", 1, [10000000] * 3, steps)
+    for c, d, w in sampler:
+        ref = float(O.train_step(phi, topt, sch, c, d, w, thr))
+    assert abs(final["cyclic"] - ref) < 2e-3 * ref, (final, ref)
+    assert abs(final["none"] - ref) > 0.02 * ref                              # the schedule is in effect (oracle: 4 %)
