@@ -91,8 +91,10 @@ class NFGR:
         self.device = device
         self.precision = precision
         self.reproducible = reproducible
-        if self.opt["Compress"].get("half", False):
-            raise NotImplementedError("Compress.half is not part of the fused SIREN path")
+        # Compress.half (main.py:388-398) is fp16 forward / backward around an fp32 optimiser step — the arithmetic of the
+        # f16 tensor-core mode (fp16 operands, fp32 master weights; here with fp32 accumulation and fp32 coordinates).
+        # What `half` changes on this path is the width rule: 2 bytes per parameter (main.py:217-220, 242-245).
+        self.half = bool(self.opt["Compress"].get("half", False))
         if self.opt["Compress"]["loss"]["name"] != "datal2":
             raise NotImplementedError(self.opt["Compress"]["loss"]["name"])  # main.py:197
         if self.opt["Module"]["phi"]["name"] not in ALL_CALC_PHI_FEATURES:
@@ -111,8 +113,9 @@ class NFGR:
     def estimate_module_size(self, ideal_bytes: float):
         phi = {k: v for k, v in self.opt["Module"]["phi"].items() if k not in ("name", "features")}
         name = self.opt["Module"]["phi"]["name"]
-        f = ALL_CALC_PHI_FEATURES[name](param_count=ideal_bytes / 4.0, **phi)
-        return f, ALL_CALC_PHI_PARAM_COUNT[name](features=f, **phi) * 4.0
+        per = 2.0 if self.half else 4.0
+        f = ALL_CALC_PHI_FEATURES[name](param_count=ideal_bytes / per, **phi)
+        return f, ALL_CALC_PHI_PARAM_COUNT[name](features=f, **phi) * per
 
     # ---- partition (main.py:484-532) ------------------------------------------------------------------------------
     def divide(self, data: np.ndarray, param_size: float, dev_volume: Optional[torch.Tensor] = None) -> List[Block]:

@@ -94,13 +94,15 @@ class SIREN(nn.Module):
         return self._group
 
     def forward(self, coords: torch.Tensor) -> torch.Tensor:
-        if coords.dtype != torch.float32:
-            raise NotImplementedError("half=True is not part of the fused SIREN path (fp32 coordinates only)")
+        if coords.dtype not in (torch.float32, torch.float16):
+            raise TypeError(f"coords must be float32 (or float16 after .half()), got {coords.dtype}")
         if not coords.is_cuda:
             raise RuntimeError("brief_pytorch_b200 has no CPU compute path: move the module and coords to CUDA")
         dims = self._group_key[1] if self._group_key is not None else (1, 1, 1)
         with torch.no_grad():
-            return self.fused_group(dims).forward(0, coords)
+            # module.half() + half coordinates (main.py:388-391, utils/misc.py:83-84): the fused kernels evaluate the given
+            # (fp16-representable) values in their own arithmetic; the result goes back in the caller's dtype
+            return self.fused_group(dims).forward(0, coords.float()).to(coords.dtype)
 
     def __deepcopy__(self, memo):
         clone = SIREN(self.coords_channel, self.data_channel, self.features, self.layers, self.w0,

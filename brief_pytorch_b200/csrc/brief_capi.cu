@@ -544,10 +544,8 @@ int ensure_wpack(BriefGroup* g, cudaStream_t st) {
 int launch_lw_fit(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st, const StepState* state);
 
 // A step's explicit index array (layout: NetDev::idx_off) for a group that holds sliding-cube samplers: cube networks
-// expand their cubes, point networks get the stream they would have drawn on chip.  host_dev_cube_ids (optional, one
-// device pointer or NULL per network): replayed cube draws instead of the network's Philox stream.
-int generate_step_indices(BriefGroup* g, const int64_t* const* host_dev_cube_ids, uint64_t seed, uint64_t step, cudaStream_t st,
-                          const StepState* state) {
+// expand the cubes their Philox stream draws, point networks get the stream they would have drawn on chip.
+int generate_step_indices(BriefGroup* g, uint64_t seed, uint64_t step, cudaStream_t st, const StepState* state) {
   for (int i = 0; i < g->n_nets; ++i) {
     const NetDev& n = g->nets[i];
     if (n.mode != BRIEF_SAMPLE_RANDOM_POINTS) continue;
@@ -558,8 +556,7 @@ int generate_step_indices(BriefGroup* g, const int64_t* const* host_dev_cube_ids
     } else {
       const long long pop = (long long)(n.d - c.len[0] + 1) * (n.h - c.len[1] + 1) * (n.w - c.len[2] + 1);
       const long long cube_vox = (long long)c.len[0] * c.len[1] * c.len[2];
-      const long long* ids = host_dev_cube_ids ? reinterpret_cast<const long long*>(host_dev_cube_ids[i]) : nullptr;
-      LAUNCH(launch_gen_indices(seed, step, state, n.stream_id, n.batch, pop, n.h, n.w, c.len[1], c.len[2], cube_vox, ids, out, st));
+      LAUNCH(launch_gen_indices(seed, step, state, n.stream_id, n.batch, pop, n.h, n.w, c.len[1], c.len[2], cube_vox, nullptr, out, st));
     }
   }
   return 0;
@@ -568,7 +565,7 @@ int generate_step_indices(BriefGroup* g, const int64_t* const* host_dev_cube_ids
 int launch_fit_kernels(BriefGroup* g, const int64_t* dev_idx, uint64_t seed, uint64_t step, cudaStream_t st,
                        const StepState* state = nullptr) {
   if (!dev_idx && g->any_cube) {
-    RC(generate_step_indices(g, nullptr, seed, step, st, state));
+    RC(generate_step_indices(g, seed, step, st, state));
     dev_idx = reinterpret_cast<const int64_t*>(g->d_gen_idx.p);
   }
   FitArgs a{};

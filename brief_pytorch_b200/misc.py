@@ -234,9 +234,8 @@ def reconstruct_flattened(data_shape: Sequence[int], sample_size: int, sample_nf
     """Evaluate the network on the dense grid of `data_shape` ([d,h,w,C] / [h,w,C]) -> fp32 tensor of that shape.
     When `sample_nf` is the forward of a fused SIREN the whole grid is produced by ONE decompress launch with
     on-chip coordinates (sample_size is then irrelevant to the result); any other callable is fed coordinate
-    chunks of `sample_size` like the reference (utils/misc.py:59-92)."""
-    if half:
-        raise NotImplementedError("half=True is not part of the fused SIREN path")
+    chunks of `sample_size` like the reference (utils/misc.py:59-92).  half=True: an fp16 tensor comes back, like the
+    reference's; the fused path still evaluates fp32 coordinates (the reference rounds them to fp16 first)."""
     *cshape, channels = [int(x) for x in data_shape]
     owner = getattr(sample_nf, "__self__", None)
     from .Networks import SIREN
@@ -244,12 +243,14 @@ def reconstruct_flattened(data_shape: Sequence[int], sample_size: int, sample_nf
         dims = tuple(cshape) if len(cshape) == 3 else (1, *cshape)
         grp = owner.fused_group(dims)
         grp.set_axes(0, coords_mode)
-        return grp.decompress("float32")[0].reshape(*cshape, channels)
+        out = grp.decompress("float32")[0].reshape(*cshape, channels)
+        return out.half() if half else out   # half=True returns an fp16 tensor like the reference (utils/misc.py:69-70)
     with torch.no_grad():
         coords = create_flattened_coords(tuple(cshape), coords_mode).to(device)
-        flat = torch.zeros((coords.shape[0], channels), device=device)
+        flat = torch.zeros((coords.shape[0], channels), device=device, dtype=torch.float16 if half else torch.float32)
         for s in range(0, coords.shape[0], sample_size):
-            flat[s:s + sample_size] = sample_nf(coords[s:s + sample_size])
+            c = coords[s:s + sample_size]
+            flat[s:s + sample_size] = sample_nf(c.half() if half else c)
     return flat.reshape(*cshape, channels)
 
 

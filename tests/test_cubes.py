@@ -170,3 +170,19 @@ def test_nfgr_sampler_choice_follows_main_py():
     cf = NFGR(o, 0, "f16")
     assert cf._sampler_name(96 ** 3, (96, 96, 96)) == "randomcube"
     assert cf._cube_config((96, 50, 96)) == (3, [8, 50, 8]) and cf._step_batch((96, 50, 96)) == 3 * 8 * 50 * 8
+
+
+def test_half_selects_the_two_byte_width_rule():
+    """Compress.half (main.py:217-220, 242-245): the byte budget buys 2-byte parameters, so the same budget gives a wider
+    network; widths and theoretical sizes equal the oracle's estimate_module_size(half=True)."""
+    from test_framework import opt as make_opt
+    from brief_pytorch_b200.CompressFramework import NFGR
+    o = make_opt()
+    o["Compress"]["half"] = True
+    cf, full = NFGR(o), NFGR(make_opt())
+    phi = {k: v for k, v in o["Module"]["phi"].items() if k != "name"}
+    for budget in (1000.0, 6516.0, 16241 * 4.0, 64976 * 4.0):
+        f, nbytes = cf.estimate_module_size(budget)
+        fo, po, so = O.estimate_module_size(budget, dict(phi), half=True)
+        assert (f, nbytes) == (fo, so) and nbytes == po * 2.0
+        assert f > full.estimate_module_size(budget)[0]

@@ -1,4 +1,5 @@
-"""The general RandomCubeSampler (main.py:38-125: windows smaller than the block, several per step) on the GPU, through the
+"""Reference options no shipped config uses, on the GPU: CyclicLR / StepLR schedules, Compress.half, and above all
+the general RandomCubeSampler (main.py:38-125: windows smaller than the block, several per step), through the
 C-ABI (brief_group_set_cube_sampler / brief_cube_indices), against tests/golden/cubes.npz — written from the unmodified
 reference by oracle/gen_golden_cubes.py — and against the oracle.  Index work is bit-exact; losses are within the
 north-star tolerances (fp32 mode 1e-4, f16 mode 1e-2, per step, with headroom for the drift of 30-40 optimiser steps)."""
@@ -198,3 +199,35 @@ def test_cyclic_lr_through_nfgr_matches_the_oracle():
         ref = float(O.train_step(phi, topt, sch, c, d, w, thr))
     assert abs(final["cyclic"] - ref) < 2e-3 * ref, (final, ref)
     assert abs(final["none"] - ref) > 0.02 * ref                              # the schedule is in effect (oracle: 4 %)
+
+
+def test_half_mode_fits_and_decodes(tmp_path):
+    """Compress.half: widths from the 2-byte rule, fit and decode through the same grouped kernels; module.half() with
+    half coordinates (main.py:388-391) and reconstruct_flattened(half=True) (utils/misc.py:69-84) return fp16 tensors."""
+    from brief_pytorch_b200 import misc, synth
+    from brief_pytorch_b200.CompressFramework import NFGR
+    o = vessel_opt()
+    o["Compress"]["divide"]["divide_type"] = "total_1_2_2"
+    o["Compress"]["param"]["filesize_ratio"] = 16
+    o["Compress"]["checkpoints"] = "none"
+    o["Compress"]["half"] = True
+    vol = synth.vessel((16, 48, 48), seed=7)
+    first, _ = NFGR(copy.deepcopy(o), 0, "auto").compress_divide(vol, None, max_steps=1)
+    cdir = str(tmp_path / "compressed")
+    cf = NFGR(o, 0, "auto")
+    blocks, _ = cf.compress_divide(vol, cdir, max_steps=60)
+    phi = {k: v for k, v in o["Module"]["phi"].items() if k != "name"}
+    for b0, b in zip(first, blocks):
+        assert b.features == O.estimate_module_size(b.param_size, dict(phi), half=True)[0]
+        assert np.isfinite(b.loss) and b.loss < b0.loss
+    out = cf.decompress_divide(os.path.join(cdir, "sideinfos.yaml"), os.path.join(cdir, "module"), os.path.join(cdir, "sideinfos"))
+    assert out.shape == vol.shape and out.dtype == vol.dtype
+    m = blocks[0].module.cuda()
+    coords = (torch.rand(257, 3, device="cuda") * 2 - 1).half()
+    y32 = m(coords.float())
+    y16 = copy.deepcopy(m).half()(coords)
+    assert y16.dtype == torch.float16 and y16.shape == (257, 1) and y32.dtype == torch.float32
+    scale = max(1.0, float(y32.abs().max()))
+    assert float((y16.float() - y32).abs().max()) < 0.05 * scale      # fp16-rounded parameters and output
+    rec = misc.reconstruct_flattened(list(blocks[0].shape) + [1], 10000, m.forward, half=True)
+    assert rec.dtype == torch.float16 and tuple(rec.shape) == tuple(blocks[0].shape) + (1,)
