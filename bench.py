@@ -179,6 +179,15 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def fit_config(plan, n_local, prec, world):
+    """`config` of the default fit line; the reference arm prints the same object (it times the same workload, its own
+    arithmetic is in `dtype` and what a step of it covers is in `cpu_baseline.sample`)."""
+    return {"workload": plan["desc"], "blocks_per_gpu": n_local, "block_shape": list(plan["block_shape"]),
+            "features": plan["features"], "layers": plan["layers"], "batch_per_block": plan["batch"],
+            "precision": prec, "l2": "flushed (256 MiB write) between timed steps",
+            "parallelism": f"blocks sharded by LPT over {world} GPU(s), no collective on the fit path"}
+
+
 def oracle_fit_rate(plan, seconds, threads):
     """The reference's CPU PyTorch path (oracle restatement of main.py:385-400 around torch CPU ops) on ONE block of
     the workload; returns (coord-samples/s, steps timed)."""
@@ -227,7 +236,7 @@ def run_reference(args, plan):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": plan["desc"], "sample": sample},
+        "config": fit_config(plan, plan["n_blocks"], "fp32" if args.precision == "fp32" else "f16", args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -983,10 +992,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": prec if prec == "f16" else "f32", "data": "synthetic",
-            "config": {"workload": plan["desc"], "blocks_per_gpu": n_local, "block_shape": list(bs),
-                       "features": plan["features"], "layers": plan["layers"], "batch_per_block": plan["batch"],
-                       "precision": prec, "l2": "flushed (256 MiB write) between timed steps",
-                       "parallelism": f"blocks sharded by LPT over {world} GPU(s), no collective on the fit path"},
+            "config": fit_config(plan, n_local, prec, world),
             "back_to_back": {"value": samples_per_step * args.steps / t_b2b, "unit": UNIT,
                              "ms_per_step": 1e3 * t_b2b / args.steps, "note": "no L2 flush, one event pair around K steps"},
             "e2e": {"value": samples_per_step * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
