@@ -227,8 +227,6 @@ class NFGR:
         np_dt = np.dtype(dtype)
         dev_raw = [b.dev if b.dev is not None else _to_device_raw(b.data[..., 0], grp.device) for b in blocks]
         weight_rules = list(C["loss"]["weight"])
-        needs_host = any(r.split("_")[0] == "exp" for r in weight_rules)
-        host_raw: Dict[int, np.ndarray] = {}
         pre = C.get("preprocess")
         if pre and not preprocessed:
             if np_dt in (np.uint8, np.uint16):

@@ -186,3 +186,53 @@ def test_half_selects_the_two_byte_width_rule():
         fo, po, so = O.estimate_module_size(budget, dict(phi), half=True)
         assert (f, nbytes) == (fo, so) and nbytes == po * 2.0
         assert f > full.estimate_module_size(budget)[0]
+
+
+def test_schedule_windows_random_milestone_lists():
+    """Any MultiStepLR list (duplicates included: torch applies gamma once per occurrence), any resume point: walking
+    the run window by window gives the C side the learning rate of torch's scheduler at every step."""
+    from brief_pytorch_b200.group import schedule_window
+    rng = np.random.default_rng(6)
+    for _ in range(60):
+        n_steps = int(rng.integers(5, 120))
+        ms = sorted(int(m) for m in rng.integers(1, n_steps + 10, size=int(rng.integers(0, 30))))
+        gamma = float(rng.choice([0.1, 0.2, 0.5, 0.9]))
+        p = torch.nn.Parameter(torch.zeros(1))
+        topt = torch.optim.SGD([p], lr=1e-3)
+        sch = torch.optim.lr_scheduler.MultiStepLR(topt, milestones=ms, gamma=gamma)
+        want = []
+        for _ in range(n_steps):
+            want.append(topt.param_groups[0]["lr"])
+            topt.step()
+            sch.step()
+        steps_done = int(rng.integers(0, n_steps))      # a resumed run starts anywhere
+        while steps_done < n_steps:
+            lr0, window, horizon = schedule_window(1e-3, ms, gamma, steps_done)
+            assert len(window) <= 8 and (horizon is None or horizon > steps_done)
+            n = n_steps - steps_done if horizon is None else min(n_steps - steps_done, horizon - steps_done)
+            for t in range(steps_done + 1, steps_done + n + 1):
+                # BriefOptConfig carries lr and gamma as C floats: 6e-8 relative per factor
+                assert abs(c_side_lr(lr0, window, gamma, t) - want[t - 1]) <= (len(ms) + 2) * 6e-8 * want[t - 1], (ms, gamma, t)
+            steps_done += n
+
+
+def test_quantile_from_histogram_is_numpys_quantile():
+    """The device path of the 'quantile' weight rule reads the two order statistics off a histogram: bit-equal to
+    np.quantile on the selected voxels for integer data, any threshold and quantile, ties included."""
+    from brief_pytorch_b200 import misc
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        top = int(rng.choice([255, 65535]))
+        n = int(rng.integers(1, 400))
+        if rng.random() < 0.5:
+            data = rng.integers(0, top + 1, size=n)
+        else:
+            data = rng.choice(rng.integers(0, top + 1, size=int(rng.integers(1, 5))), size=n)
+        ge = float(rng.choice([0, int(np.median(data)), int(data.max()), rng.integers(0, top + 1), 0.5 + int(data.min())]))
+        q = float(rng.choice([0.0, 1.0, 0.5, np.round(rng.uniform(0, 1), 3)]))
+        sel = data[data >= ge]
+        got = misc.quantile_from_histogram(np.bincount(data, minlength=top + 1), ge, q)
+        if sel.size == 0:
+            assert np.isnan(got)
+        else:
+            assert got == float(np.quantile(sel, q)), (top, n, ge, q)
