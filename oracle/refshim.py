@@ -99,9 +99,10 @@ def load_reference() -> types.SimpleNamespace:
 
 
 def load_main_samplers() -> types.SimpleNamespace:
-    """The LIVE sampler classes of the reference, main.py:38-163.  main.py cannot be imported (argparse / OmegaConf
-    globals at module level), so the two class definitions are cut out of its syntax tree and executed unmodified in a
-    namespace that holds exactly the names they use (torch, np, rearrange, typing, utils.dataset.create_*coords)."""
+    """The LIVE sampler classes (main.py:38-163) and loss (main.py:176-182) of the reference.  main.py cannot be imported
+    (argparse / OmegaConf globals at module level), so these definitions are cut out of its syntax tree and executed
+    unmodified in a namespace that holds exactly the names they use (torch, np, F, rearrange, typing,
+    utils.dataset.create_*coords)."""
     import ast
     load_reference()
     with open(os.path.join(REFERENCE_ROOT, "main.py")) as fh:
@@ -112,4 +113,10 @@ def load_main_samplers() -> types.SimpleNamespace:
     for node in tree.body:
         if isinstance(node, ast.ClassDef) and node.name in ("RandomCubeSampler", "RandompointSampler"):
             exec(compile(ast.Module([node], []), os.path.join(REFERENCE_ROOT, "main.py"), "exec"), ns)
-    return types.SimpleNamespace(RandomCubeSampler=ns["RandomCubeSampler"], RandompointSampler=ns["RandompointSampler"])
+    # the loss is a closure inside NFGR.set_loss (main.py:176-182); it uses nothing but torch.nn.functional as F
+    exec("import torch.nn.functional as F\n", ns)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "datal2":
+            exec(compile(ast.Module([node], []), os.path.join(REFERENCE_ROOT, "main.py"), "exec"), ns)
+    return types.SimpleNamespace(RandomCubeSampler=ns["RandomCubeSampler"], RandompointSampler=ns["RandompointSampler"],
+                                 datal2=ns["datal2"])

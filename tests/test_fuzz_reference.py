@@ -185,3 +185,118 @@ def test_model_files_round_trip_both_ways(ref, tmp_path):
         ref.ModelSave.load_model(fresh_theirs, a)
         for p, q, r in zip(ours.parameters(), fresh_ours.parameters(), fresh_theirs.parameters()):
             assert p.detach().numpy().tobytes() == q.detach().numpy().tobytes() == r.detach().numpy().tobytes()
+
+
+def test_oracle_training_loop_is_the_references_bit_for_bit(ref):
+    """The oracle's restatement of the loop main.py:385-400 (init, sampler, loss, optimiser, scheduler) against the
+    reference's own pieces — utils.Networks.init_phi, the live sampler classes and datal2 closure cut out of main.py,
+    utils.misc.configure_optimizer / configure_lr_scheduler — on random small configurations: every loss and every
+    parameter after four steps identical to the bit.  This is what makes the oracle a stand-in for the reference where
+    the reference cannot travel (the GPU box)."""
+    import brief_oracle as O
+    live = refshim.load_main_samplers()
+    rng = np.random.default_rng(106)
+    for case in range(max(6, ROUNDS // 4)):
+        vol = rand_volume(rng, lo=5, hi=12)
+        top = 255 if vol.dtype == np.uint8 else 65535
+        if vol.max() == vol.min():
+            continue
+        kw = dict(coords_channel=3, data_channel=1, layers=int(rng.integers(2, 8)), w0=float(rng.choice([10, 20, 30])),
+                  features=int(rng.integers(2, 24)), name="SIREN", output_act=False, res=False)
+        optname = str(rng.choice(["Adamax", "Adam", "SGD"]))
+        sched = [{"name": "MultiStepLR", "milestones": [1, 3], "gamma": 0.2}, {"name": "StepLR", "step_size": 2, "gamma": 0.5},
+                 {"name": "none"}][int(rng.integers(0, 3))]
+        rules = [[f"value_{top // 4}_{top}_0.1"], ["none"], [f"exp_{top // 2}_0.5"]][int(rng.integers(0, 3))]
+        thres = float(rng.choice([0, top // 3, top]))
+        cube = bool(rng.integers(0, 2))
+        clen = [int(rng.integers(1, s + 3)) for s in vol.shape[:3]]
+        count, batch, seed = int(rng.integers(1, 4)), int(rng.integers(1, 300)), int(rng.integers(0, 1000))
+
+        def run(side):
+            N, M, IO, S, loss_fn = ((ref.Networks, ref.misc, ref.io, live, live.datal2) if side == "ref"
+                                    else (O, O, O, O, O.datal2))
+            weight = M.parse_weight(vol.copy(), rules)
+            data_t, info = IO.normalize_data(vol.copy(), "minmaxany_0_100")
+            tau = float(IO.normalize_data(np.array(thres), "minmaxany_0_100", max=info["max"], min=info["min"])[0])
+            torch.manual_seed(seed)
+            phi = N.init_phi(dict(kw))
+            opt = M.configure_optimizer(phi.parameters(), optname, 1e-3)
+            sch = M.configure_lr_scheduler(opt, sched)
+            sampler = (S.RandomCubeSampler(data_t, weight, "-1,1", count, list(clen), 4) if cube
+                       else S.RandompointSampler(data_t, weight, "-1,1", batch, 4))
+            losses = []
+            for c, d, w in sampler:           # main.py:385-400
+                opt.zero_grad()
+                loss = loss_fn(d, phi.forward(c), w, tau)
+                loss.backward()
+                opt.step()
+                sch.step()
+                losses.append(float(loss.detach()))
+            return losses, [p.detach().numpy().copy() for p in phi.parameters()]
+
+        l_ref, p_ref = run("ref")
+        l_ora, p_ora = run("oracle")
+        assert l_ref == l_ora, (case, kw, optname, sched, rules)
+        for a, b in zip(p_ref, p_ora):
+            assert a.tobytes() == b.tobytes(), (case, kw, optname)
+
+
+def test_oracle_decode_partition_preprocess_against_reference(ref, tmp_path):
+    """The rest of the oracle against the reference on random inputs: dense decode (reconstruct_flattened +
+    invnormalize_data), model files, partition / budgets / merge, preprocess (scipy call and the scipy-free restatement)."""
+    import brief_oracle as O
+    rng = np.random.default_rng(107)
+    varied = 0
+    for case in range(max(6, ROUNDS // 4)):
+        vol = rand_volume(rng, "uint16", lo=4, hi=12)
+        if vol.max() == vol.min():
+            continue
+        kw = dict(coords_channel=3, data_channel=1, layers=int(rng.integers(2, 7)), w0=float(rng.choice([10, 20])),
+                  features=int(rng.integers(2, 20)), name="SIREN", output_act=False, res=False)
+        seed = int(rng.integers(0, 1000))
+        torch.manual_seed(seed)
+        phi_r = ref.Networks.init_phi(dict(kw))
+        torch.manual_seed(seed)
+        phi_o = O.init_phi(dict(kw))
+        with torch.no_grad():                 # spread the outputs over the whole 0..100 range and beyond
+            for phi in (phi_r, phi_o):
+                phi.net[-1][0].weight.mul_(3000.0)
+                phi.net[-1][0].bias.fill_(50.0)
+        _, side = ref.io.normalize_data(vol.copy(), "minmaxany_0_100")
+        side = dict(side, data_shape=list(vol.shape), phi_features=kw["features"], phi_name="SIREN")
+        chunk = int(rng.choice([7, 100, 10000]))
+        with torch.no_grad():
+            rec = ref.misc.reconstruct_flattened(side["data_shape"], chunk, phi_r.forward, device="cpu", coords_mode="-1,1").float().cpu()
+        want = ref.io.invnormalize_data(rec.clone(), side, "minmaxany_0_100")
+        got = O.decompress_block(phi_o, side, "minmaxany_0_100", sample_size=chunk)
+        np.testing.assert_array_equal(got, want)
+        varied += len(np.unique(want)) > 2
+        # model files: written by one, read by the other
+        a, b = str(tmp_path / f"r{case}"), str(tmp_path / f"o{case}")
+        ref.ModelSave.save_model(phi_r, a)
+        O.save_model(phi_o, b)
+        for name in sorted(os.listdir(a)):
+            assert open(os.path.join(a, name), "rb").read() == open(os.path.join(b, name), "rb").read()
+        # partition / budgets / merge
+        n = [int(rng.integers(1, min(3, s) + 1)) for s in vol.shape[:3]]
+        kind = f"total_{n[0]}_{n[1]}_{n[2]}"
+        theirs = ref.misc.divide_data(vol.copy(), kind)
+        theirs = theirs[0] if isinstance(theirs, tuple) else theirs
+        ours = O.divide_data(vol.copy(), kind)
+        assert [c["name"] for c in ours] == [c["name"] for c in theirs]
+        np.testing.assert_array_equal(O.merge_divided_data(ours, vol.shape), ref.misc.merge_divided_data(theirs, vol.shape))
+        for alloc in ("equal", "by_size", "by_var"):
+            try:
+                w_ = ref.misc.alloc_param([dict(c) for c in theirs], 50000.0, alloc, 26.0)
+            except Exception:
+                continue
+            g_ = O.alloc_param([dict(c) for c in ours], 50000.0, alloc, 26.0)
+            np.testing.assert_array_equal([float(c["param_size"]) for c in g_], [float(c["param_size"]) for c in w_])
+        # preprocess
+        level = int(np.quantile(vol, rng.uniform(0.05, 0.6)))
+        close = False if rng.random() < 0.25 else [int(x) for x in rng.integers(1, 4, size=3)]
+        clip = [int(rng.integers(0, 1000)), int(rng.integers(30000, 65536))]
+        want = ref.misc.preprocess(vol.copy(), level, close, clip)
+        np.testing.assert_array_equal(O.preprocess(vol.copy(), level, close, clip), want)
+        np.testing.assert_array_equal(O.preprocess_restated(vol.copy(), level, close, clip), want)
+    assert varied >= 3   # the decodes were not all saturated
